@@ -251,3 +251,50 @@ def iir_order(sos):
     """``multirate_IIR.__init__`` order bookkeeping (multirate_helper.py:163-164)."""
     sos = np.asarray(sos)
     return np.sum(np.sign(np.abs(sos[:, 2]))) + np.sum(np.sign(np.abs(sos[:, 1])))
+
+
+# --------------------------------------------------------------------------- CPU baseline helpers
+# (bench.py cpu_baseline / --impl reference legs only)
+_BASE_CACHE = {}
+
+
+def _baseline_chunk(task):
+    """Worker: one halo-chunk of the reference FIR call on its own seeded complex64 data.
+    The input is generated once per worker and cached so that timed passes measure
+    ``np.convolve`` (what lfilter's FIR branch executes, in complex128) and nothing else."""
+    seed, n, b_bytes = task
+    b = np.frombuffer(b_bytes, dtype=np.float64)
+    key = (seed, n)
+    x = _BASE_CACHE.get(key)
+    if x is None:
+        rng = np.random.default_rng(seed)
+        x = (rng.standard_normal(n + len(b) - 1, dtype=np.float32)
+             + 1j * rng.standard_normal(n + len(b) - 1, dtype=np.float32)).astype(np.complex64)
+        _BASE_CACHE.clear()
+        _BASE_CACHE[key] = x
+    K = len(b)
+    y = fir_filter(b, x[K - 1:], hist=x[:K - 1])         # np.convolve in complex128
+    return float(np.abs(y[:16]).sum())
+
+
+class FirCpuBaseline:
+    """All-cores run of the reference's FIR arithmetic on halo-chunks:
+    ``cores`` worker processes, each filtering ``chunk`` complex64 samples per pass."""
+
+    def __init__(self, b, cores=None, chunk=1 << 21):
+        import multiprocessing as mp
+        import os
+        self.cores = cores or len(os.sched_getaffinity(0))
+        self.chunk = chunk
+        self.b_bytes = np.asarray(b, dtype=np.float64).tobytes()
+        self.pool = mp.get_context("spawn").Pool(self.cores)
+        self.tasks = [(1000 + i, chunk, self.b_bytes) for i in range(self.cores)]
+        self.samples_per_pass = self.cores * chunk
+        self.run_pass()                                    # generate inputs, warm numpy
+
+    def run_pass(self):
+        return self.pool.map(_baseline_chunk, self.tasks, chunksize=1)
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()

@@ -1,0 +1,346 @@
+// fir_direct.cu -- tiled direct-form / polyphase FIR on CUDA cores (sm_100a).
+//
+// One kernel template covers the three FIR entry points of the reference's multirate_FIR
+// (src/sk_dsp_comm/multirate_helper.py:104-127):
+//   filter : y[i]      = sum_k b[k]      x[i-k]                       (L = M = 1)
+//   up(L)  : y[L m + r] = sum_q L b[Lq+r] x[m-q]        r in [0,L)     (polyphase interpolation)
+//   dn(M)  : y[m]      = sum_c sum_q b[Mq+c] x[M(m-q)-c]  c in [0,M)   (polyphase decimation)
+// In all three the inner work is "sum_q h[q] * xin[m-q]" over a unit-stride phase stream, so a
+// block stages, per tile of TILE = NT*R consecutive m positions,
+//   * the tap phases h_ph[q] (zero padded to KQ, a multiple of R) in shared memory,
+//   * the M input phase streams xin_c[m] = x[M m - c] (one stream for filter / up), each with a
+//     KQ-sample left apron, de-interleaved while they are loaded with coalesced reads,
+// and every thread produces R consecutive outputs with a register sliding window: per tap
+// it issues R (complex: 2R) FMAs against ONE new shared-memory sample, so the FMA pipe -- not
+// the LSU / shared-memory port -- is the limiter (DESIGN.md "FIR kernel" has the arithmetic).
+// Shared-memory rows are padded by one sample every R samples so that the R-strided
+// per-lane window accesses are bank-conflict free.  Results leave through a shared-memory
+// transpose so global stores are fully coalesced.
+#include "common.cuh"
+
+namespace b200dsp {
+
+template <typename S, typename C>
+struct FirArgs {
+    const S *x;
+    const S *hist;
+    S *y;
+    const C *taps;     // ntaps raw taps (device)
+    int64_t n_in;      // input samples
+    int64_t n_m;       // m-domain length: filter n, up n, dn floor(n/M)
+    int32_t ntaps;
+    int32_t kq;        // taps per phase, padded to a multiple of R
+    int32_t hist_len;  // samples available in hist (logically x[-hist_len..-1])
+    int32_t L, M;      // at most one of them > 1
+    int32_t lg;        // output phases staged per store group (1 <= lg <= L)
+};
+
+template <int R>
+__device__ __forceinline__ int pad_idx(int i) { return i + i / R; }
+
+template <typename C> struct __align__(16) TapVec { C v[16 / sizeof(C)]; };
+
+template <typename S, typename C, int R, int NT>
+__global__ void __launch_bounds__(NT) fir_poly_kernel(const FirArgs<S, C> a)
+{
+    constexpr int TILE = NT * R;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int kq = a.kq;
+    const int P = a.L * a.M;                        // number of tap phases
+    const int len_ph = TILE + kq;                   // samples per staged input phase
+    const int PS = pad_idx<R>(len_ph) + 1;          // padded phase stride
+    C *hs = reinterpret_cast<C *>(smem_raw);
+    size_t taps_bytes = ((size_t)P * kq * sizeof(C) + 15) & ~(size_t)15;
+    S *xs = reinterpret_cast<S *>(smem_raw + taps_bytes);
+    S *st = (a.L == 1) ? xs : xs + (size_t)a.M * PS;   // staging aliases xs when there is one group
+
+    const int64_t m_t = (int64_t)blockIdx.x * TILE;
+
+    // ---- stage tap phases: h[ph][q] = L * b[P q + ph] (zero padded) ----
+    {
+        const C gain = (C)a.L;
+        for (int v = tid; v < P * kq; v += NT) {
+            int ph = v / kq, q = v - ph * kq;
+            int64_t k = (int64_t)q * P + ph;
+            hs[v] = (k < a.ntaps) ? gain * a.taps[k] : (C)0;
+        }
+    }
+    // ---- stage input phases (coalesced over the contiguous global range) ----
+    {
+        const int M = a.M;
+        const int total = M * len_ph;
+        const int64_t g_base = (int64_t)M * (m_t - kq) - (M - 1);
+        for (int v = tid; v < total; v += NT) {
+            int i = (M == 1) ? v : v / M;
+            int c = (M == 1) ? 0 : (M - 1 - (v - i * M));
+            int64_t g = g_base + v;
+            S val = zero_of(S());
+            if (g >= 0) {
+                if (g < a.n_in) val = a.x[g];
+            } else if (a.hist != nullptr) {
+                int64_t hidx = (int64_t)a.hist_len + g;
+                if (hidx >= 0) val = a.hist[hidx];
+            }
+            xs[(size_t)c * PS + pad_idx<R>(i)] = val;
+        }
+    }
+    __syncthreads();
+
+    const int nkb = kq / R;
+    // first window group of this thread: padded index of sample (kq + tid*R)
+    const int grp0 = (nkb + tid) * (R + 1);
+
+    for (int rg = 0; rg < a.L; rg += a.lg) {
+        const int lgc = min(a.lg, a.L - rg);
+        for (int rr = 0; rr < lgc; ++rr) {
+            S acc[R];
+#pragma unroll
+            for (int j = 0; j < R; ++j) acc[j] = zero_of(S());
+
+            for (int c = 0; c < a.M; ++c) {
+                const int ph = (a.L > 1) ? (rg + rr) : c;
+                const C *h = hs + ph * kq;
+                const S *xc = xs + (size_t)c * PS;
+                S w[R];
+                // slots 1..R-1 <- x[m0+1 .. m0+R-1]
+#pragma unroll
+                for (int s = 1; s < R; ++s) w[s] = xc[grp0 + s];
+                const S *gp = xc + grp0;     // group holding x[m0 - kb*R]
+                for (int kb = 0; kb < nkb; ++kb) {
+                    constexpr int TV = 16 / (int)sizeof(C);      // taps per 16-byte broadcast load
+#pragma unroll
+                    for (int k4 = 0; k4 < R; k4 += TV) {
+                        const TapVec<C> tv = *reinterpret_cast<const TapVec<C> *>(h + kb * R + k4);
+#pragma unroll
+                        for (int u = 0; u < TV; ++u) {
+                            const int kk = k4 + u;
+                            // new sample x[m0 - (kb*R+kk)] -> slot (R-kk)%R
+                            w[(R - kk) % R] = (kk == 0) ? gp[0] : gp[-1 - kk];
+                            const C t = tv.v[u];
+#pragma unroll
+                            for (int j = 0; j < R; ++j) tap_fma(acc[j], t, w[(j - kk + R) % R]);
+                        }
+                    }
+                    gp -= (R + 1);
+                }
+            }
+            if (a.L == 1) __syncthreads();      // xs is dead: staging may overwrite it
+#pragma unroll
+            for (int j = 0; j < R; ++j) st[pad_idx<R>((tid * R + j) * lgc + rr)] = acc[j];
+        }
+        __syncthreads();
+        // ---- coalesced store of this phase group ----
+        const int total_o = TILE * lgc;
+        for (int u = tid; u < total_o; u += NT) {
+            int m = (lgc == 1) ? u : u / lgc;
+            int r2 = (lgc == 1) ? 0 : (u - m * lgc);
+            int64_t mg = m_t + m;
+            if (mg < a.n_m) a.y[mg * a.L + rg + r2] = st[pad_idx<R>(u)];
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+struct b200dsp_fir_plan_impl {
+    int32_t ntaps;
+    float *taps_f32;
+    double *taps_f64;
+};
+
+static thread_local int g_fir_variant = 0;
+
+template <typename S, int R, int NT>
+static int launch_fir(const b200dsp_fir_plan_impl *p, const void *x, const void *hist, void *y,
+                      int64_t n, int64_t n_m, int32_t L, int32_t M, int32_t hist_len,
+                      cudaStream_t stream)
+{
+    using C = typename Sample<S>::C;
+    constexpr int TILE = NT * R;
+    FirArgs<S, C> a;
+    a.x = static_cast<const S *>(x);
+    a.hist = static_cast<const S *>(hist);
+    a.y = static_cast<S *>(y);
+    a.taps = sizeof(C) == 4 ? reinterpret_cast<const C *>(p->taps_f32)
+                            : reinterpret_cast<const C *>(p->taps_f64);
+    a.n_in = n;
+    a.n_m = n_m;
+    a.ntaps = p->ntaps;
+    const int P = L * M;
+    int taps_per_phase = (p->ntaps + P - 1) / P;
+    a.kq = ((taps_per_phase + R - 1) / R) * R;
+    a.hist_len = hist_len;
+    a.L = L;
+    a.M = M;
+    const int len_ph = TILE + a.kq;
+    const size_t PS = (size_t)(len_ph + len_ph / R) + 1;
+    const size_t taps_bytes = ((size_t)P * a.kq * sizeof(C) + 15) & ~(size_t)15;
+    const size_t xs_bytes = (size_t)M * PS * sizeof(S);
+    size_t smem;
+    if (L == 1) {
+        a.lg = 1;
+        size_t st_bytes = (size_t)(TILE + TILE / R + 1) * sizeof(S);
+        smem = taps_bytes + (xs_bytes > st_bytes ? xs_bytes : st_bytes);
+    } else {
+        if (taps_bytes + xs_bytes + (size_t)(TILE + TILE / R + 1) * sizeof(S) > kMaxSmemPerBlock)
+            return B200DSP_E_UNSUPPORTED;
+        size_t room = kMaxSmemPerBlock - taps_bytes - xs_bytes;
+        // keep the staging area modest so several blocks stay resident per SM
+        size_t budget = room < 96 * 1024 ? room : 96 * 1024;
+        int lg = (int)(budget / ((size_t)(TILE + TILE / R + 1) * sizeof(S)));
+        if (lg < 1) lg = 1;
+        if (lg > L) lg = L;
+        a.lg = lg;
+        size_t st_elems = (size_t)TILE * lg;
+        smem = taps_bytes + xs_bytes + (st_elems + st_elems / R + 1) * sizeof(S);
+    }
+    if (smem > kMaxSmemPerBlock) return B200DSP_E_UNSUPPORTED;
+    auto kern = fir_poly_kernel<S, C, R, NT>;
+    B200_CHECK_CUDA(allow_smem(kern, smem));
+    int64_t tiles = (n_m + TILE - 1) / TILE;
+    if (tiles > 2147483647LL) {
+        set_error("fir: too many tiles (%lld)", (long long)tiles);
+        return B200DSP_E_UNSUPPORTED;
+    }
+    kern<<<(unsigned)tiles, NT, smem, stream>>>(a);
+    B200_CHECK_LAUNCH("fir_poly_kernel");
+    return B200DSP_OK;
+}
+
+// Try progressively smaller tiles until the staging fits in shared memory.
+template <typename S, int R>
+static int launch_fir_fit(const b200dsp_fir_plan_impl *p, const void *x, const void *hist, void *y,
+                          int64_t n, int64_t n_m, int32_t L, int32_t M, int32_t hist_len,
+                          cudaStream_t stream, int nt_first)
+{
+    int rc = B200DSP_E_UNSUPPORTED;
+    if (nt_first >= 256) {
+        rc = launch_fir<S, R, 256>(p, x, hist, y, n, n_m, L, M, hist_len, stream);
+        if (rc != B200DSP_E_UNSUPPORTED) return rc;
+    }
+    if (nt_first >= 128) {
+        rc = launch_fir<S, R, 128>(p, x, hist, y, n, n_m, L, M, hist_len, stream);
+        if (rc != B200DSP_E_UNSUPPORTED) return rc;
+    }
+    rc = launch_fir<S, R, 64>(p, x, hist, y, n, n_m, L, M, hist_len, stream);
+    if (rc != B200DSP_E_UNSUPPORTED) return rc;
+    rc = launch_fir<S, R, 32>(p, x, hist, y, n, n_m, L, M, hist_len, stream);
+    if (rc == B200DSP_E_UNSUPPORTED)
+        set_error("fir: filter (%d taps, L=%d, M=%d) too long for on-chip staging", p->ntaps, L, M);
+    return rc;
+}
+
+static int fir_dispatch(const b200dsp_fir_plan_impl *p, int dtype, const void *x, const void *hist,
+                        void *y, int64_t n, int64_t n_m, int32_t L, int32_t M, int32_t hist_len,
+                        cudaStream_t s)
+{
+    const int v = g_fir_variant;
+    switch (dtype) {
+    case B200DSP_F32:
+        if (v == 1) return launch_fir_fit<float, 16>(p, x, hist, y, n, n_m, L, M, hist_len, s, 256);
+        return launch_fir_fit<float, 32>(p, x, hist, y, n, n_m, L, M, hist_len, s, 128);
+    case B200DSP_C64:
+        if (v == 1) return launch_fir_fit<float2, 16>(p, x, hist, y, n, n_m, L, M, hist_len, s, 256);
+        if (v == 2) return launch_fir_fit<float2, 16>(p, x, hist, y, n, n_m, L, M, hist_len, s, 128);
+        return launch_fir_fit<float2, 32>(p, x, hist, y, n, n_m, L, M, hist_len, s, 128);
+    case B200DSP_F64:
+        return launch_fir_fit<double, 16>(p, x, hist, y, n, n_m, L, M, hist_len, s, 128);
+    case B200DSP_C128:
+        return launch_fir_fit<double2, 8>(p, x, hist, y, n, n_m, L, M, hist_len, s, 128);
+    default:
+        set_error("fir: bad dtype code %d", dtype);
+        return B200DSP_E_DTYPE;
+    }
+}
+
+}  // namespace b200dsp
+
+using namespace b200dsp;
+
+struct b200dsp_fir_plan : b200dsp_fir_plan_impl {};
+
+extern "C" {
+
+int b200dsp_fir_plan_create(const double *taps_host, int32_t ntaps, b200dsp_fir_plan **plan)
+{
+    if (!taps_host || !plan || ntaps < 1) {
+        set_error("fir_plan_create: bad argument (ntaps=%d)", ntaps);
+        return B200DSP_E_BADARG;
+    }
+    b200dsp_fir_plan *p = new b200dsp_fir_plan();
+    p->ntaps = ntaps;
+    p->taps_f32 = nullptr;
+    p->taps_f64 = nullptr;
+    float *tmp = new float[ntaps];
+    for (int i = 0; i < ntaps; ++i) tmp[i] = (float)taps_host[i];
+    cudaError_t e = cudaMalloc(&p->taps_f32, sizeof(float) * ntaps);
+    if (e == cudaSuccess) e = cudaMalloc(&p->taps_f64, sizeof(double) * ntaps);
+    if (e == cudaSuccess) e = cudaMemcpy(p->taps_f32, tmp, sizeof(float) * ntaps, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(p->taps_f64, taps_host, sizeof(double) * ntaps, cudaMemcpyHostToDevice);
+    delete[] tmp;
+    if (e != cudaSuccess) {
+        set_error("fir_plan_create: %s", cudaGetErrorString(e));
+        cudaFree(p->taps_f32);
+        cudaFree(p->taps_f64);
+        delete p;
+        return B200DSP_E_CUDA;
+    }
+    *plan = p;
+    return B200DSP_OK;
+}
+
+void b200dsp_fir_plan_destroy(b200dsp_fir_plan *plan)
+{
+    if (!plan) return;
+    cudaFree(plan->taps_f32);
+    cudaFree(plan->taps_f64);
+    delete plan;
+}
+
+int32_t b200dsp_fir_plan_ntaps(const b200dsp_fir_plan *plan) { return plan ? plan->ntaps : 0; }
+
+int b200dsp_fir_filter(const b200dsp_fir_plan *plan, int dtype, const void *x, const void *hist,
+                       void *y, int64_t n, void *stream)
+{
+    if (!plan || n < 0 || (n > 0 && (!x || !y))) {
+        set_error("fir_filter: bad argument");
+        return B200DSP_E_BADARG;
+    }
+    if (n == 0) return B200DSP_OK;
+    return fir_dispatch(plan, dtype, x, hist, y, n, n, 1, 1, plan->ntaps - 1, (cudaStream_t)stream);
+}
+
+int32_t b200dsp_fir_up_hist_len(const b200dsp_fir_plan *plan, int32_t L)
+{
+    if (!plan || L < 1) return 0;
+    return (plan->ntaps - 1 + L - 1) / L;
+}
+
+int b200dsp_fir_up(const b200dsp_fir_plan *plan, int dtype, const void *x, const void *hist,
+                   void *y, int64_t n, int32_t L, void *stream)
+{
+    if (!plan || n < 0 || L < 1 || (n > 0 && (!x || !y))) {
+        set_error("fir_up: bad argument (L=%d)", L);
+        return B200DSP_E_BADARG;
+    }
+    if (n == 0) return B200DSP_OK;
+    return fir_dispatch(plan, dtype, x, hist, y, n, n, L, 1, b200dsp_fir_up_hist_len(plan, L),
+                        (cudaStream_t)stream);
+}
+
+int b200dsp_fir_dn(const b200dsp_fir_plan *plan, int dtype, const void *x, const void *hist,
+                   void *y, int64_t n, int32_t M, void *stream)
+{
+    if (!plan || n < 0 || M < 1 || (n > 0 && (!x || !y))) {
+        set_error("fir_dn: bad argument (M=%d)", M);
+        return B200DSP_E_BADARG;
+    }
+    int64_t n_m = n / M;
+    if (n_m == 0) return B200DSP_OK;
+    return fir_dispatch(plan, dtype, x, hist, y, n, n_m, 1, M, plan->ntaps - 1, (cudaStream_t)stream);
+}
+
+void b200dsp_set_fir_variant(int variant) { g_fir_variant = variant; }
+
+}  // extern "C"

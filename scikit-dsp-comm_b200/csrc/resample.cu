@@ -1,0 +1,115 @@
+// resample.cu -- integer zero-stuffing / decimation index maps (sm_100a), bit exact.
+// Replaces sigsys.upsample / sigsys.downsample (src/sk_dsp_comm/sigsys.py:3031-3083).
+// Both are pure HBM streaming: grids are sized to a multiple of the SM count and every
+// thread moves whole elements (4/8/16 bytes) with coalesced accesses on the dense side.
+#include "common.cuh"
+
+namespace b200dsp {
+
+// y[i*L] = x[i]; other outputs zero.  One thread per OUTPUT element so the writes (the
+// L-times larger side) are perfectly coalesced; reads hit the same x element L times in a row
+// (served by L1/L2).
+template <typename E>
+__global__ void __launch_bounds__(256) upsample_kernel(const E *__restrict__ x, E *__restrict__ y,
+                                                      int64_t n_out, int32_t L)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n_out; o += stride) {
+        int64_t q = o / L;
+        E v = zero_of(E());
+        if (q * L == o) v = x[q];
+        y[o] = v;
+    }
+}
+
+// y[m] = x[m*M + p]
+template <typename E>
+__global__ void __launch_bounds__(256) downsample_kernel(const E *__restrict__ x, E *__restrict__ y,
+                                                        int64_t n_out, int32_t M, int32_t p)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n_out; o += stride)
+        y[o] = x[o * M + p];
+}
+
+static unsigned grid_for(int64_t n, int sm_count)
+{
+    int64_t blocks = (n + 255) / 256;
+    int64_t cap = (int64_t)sm_count * 16;          // 16 resident 256-thread blocks per SM at most
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (unsigned)blocks;
+}
+
+static int sm_count_cached()
+{
+    static thread_local int dev_cached = -1, sms = 148;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev != dev_cached) {
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        dev_cached = dev;
+    }
+    return sms;
+}
+
+template <typename E>
+static int up_launch(const void *x, void *y, int64_t n, int32_t L, cudaStream_t st)
+{
+    int64_t n_out = n * L;
+    upsample_kernel<E><<<grid_for(n_out, sm_count_cached()), 256, 0, st>>>((const E *)x, (E *)y, n_out, L);
+    B200_CHECK_LAUNCH("upsample_kernel");
+    return B200DSP_OK;
+}
+
+template <typename E>
+static int dn_launch(const void *x, void *y, int64_t n_out, int32_t M, int32_t p, cudaStream_t st)
+{
+    downsample_kernel<E><<<grid_for(n_out, sm_count_cached()), 256, 0, st>>>((const E *)x, (E *)y, n_out, M, p);
+    B200_CHECK_LAUNCH("downsample_kernel");
+    return B200DSP_OK;
+}
+
+}  // namespace b200dsp
+
+using namespace b200dsp;
+
+extern "C" {
+
+int b200dsp_upsample(int dtype, const void *x, void *y, int64_t n, int32_t L, void *stream)
+{
+    if (n < 0 || L < 1 || (n > 0 && (!x || !y))) {
+        set_error("upsample: bad argument (L=%d)", L);
+        return B200DSP_E_BADARG;
+    }
+    if (n == 0) return B200DSP_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+    case B200DSP_F32: return up_launch<float>(x, y, n, L, st);
+    case B200DSP_F64: return up_launch<double>(x, y, n, L, st);
+    case B200DSP_C64: return up_launch<float2>(x, y, n, L, st);
+    case B200DSP_C128: return up_launch<double2>(x, y, n, L, st);
+    }
+    set_error("upsample: bad dtype code %d", dtype);
+    return B200DSP_E_DTYPE;
+}
+
+int b200dsp_downsample(int dtype, const void *x, void *y, int64_t n, int32_t M, int32_t p, void *stream)
+{
+    if (n < 0 || M < 1 || p < 0 || p >= M || (n > 0 && (!x || !y))) {
+        set_error("downsample: bad argument (M=%d, p=%d)", M, p);
+        return B200DSP_E_BADARG;
+    }
+    int64_t n_out = n / M;
+    if (n_out == 0) return B200DSP_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+    case B200DSP_F32: return dn_launch<float>(x, y, n_out, M, p, st);
+    case B200DSP_F64: return dn_launch<double>(x, y, n_out, M, p, st);
+    case B200DSP_C64: return dn_launch<float2>(x, y, n_out, M, p, st);
+    case B200DSP_C128: return dn_launch<double2>(x, y, n_out, M, p, st);
+    }
+    set_error("downsample: bad dtype code %d", dtype);
+    return B200DSP_E_DTYPE;
+}
+
+}  // extern "C"

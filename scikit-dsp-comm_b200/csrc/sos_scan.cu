@@ -1,0 +1,675 @@
+// sos_scan.cu -- second-order-section IIR cascade as a parallel-prefix recurrence (sm_100a).
+//
+// Replaces scipy.signal.sosfilt as called by the reference's multirate_IIR
+// (src/sk_dsp_comm/multirate_helper.py:169-192).  sosfilt is a strictly sequential
+// direct-form-II-transposed loop; here the same recurrence is evaluated in
+// three launches per group of <= 8 sections:
+//
+//   K1 sos_pass1   one block per tile of T = 512*LC samples.  The tile is staged in shared
+//                  memory TRANSPOSED (sample n of chunk t at [n][t]) so that thread t can walk
+//                  its own LC-sample chunk with conflict-free accesses.  Each thread runs the
+//                  cascade over its chunk from ZERO state and keeps the 2*nsec final state
+//                  values ("chunk carry").  A Kogge-Stone scan over the 512 carries with the
+//                  constant matrices A^(LC*2^j) (the cascade is LTI, so only state VECTORS are
+//                  scanned, never matrices) yields the tile carry.  Chunk carries and the
+//                  tile carry go to the workspace.
+//   K2 sos_tile_scan   one block: scans the tile carries with A^T (runs of r tiles per
+//                  thread + Kogge-Stone over the runs) -> true state at every tile start.
+//   K3 sos_pass2   one block per tile: re-loads the tile, scans the stored chunk carries
+//                  with the tile's true start state folded in, then every thread re-runs the
+//                  cascade over its chunk from its TRUE start state and writes the outputs
+//                  (through the same transposed tile -> coalesced stores).
+//
+// Up-sampling (zero stuffing, x L gain) is fused into the tile load and down-sampling into
+// the tile store, so multirate_IIR.up/.dn never materialise the full-rate stream.
+#include "common.cuh"
+#include <vector>
+
+namespace b200dsp {
+
+constexpr int SOS_NT = 512;          // threads per block in K1/K3
+constexpr int SOS_LEVELS = 9;        // log2(SOS_NT)
+constexpr int SOS_MAXSEC = 8;        // sections per launch group
+constexpr int SOS_K2_NT = 256;       // threads in the tile-scan block
+constexpr int SOS_K2_LEVELS = 8;
+
+template <typename S> struct SosCfg;
+template <> struct SosCfg<float>   { static constexpr int LC = 64; static constexpr int LCI = 2; };
+template <> struct SosCfg<double>  { static constexpr int LC = 32; static constexpr int LCI = 1; };
+template <> struct SosCfg<float2>  { static constexpr int LC = 32; static constexpr int LCI = 1; };
+template <> struct SosCfg<double2> { static constexpr int LC = 16; static constexpr int LCI = 0; };
+// LCI indexes the plan's per-LC matrix sets: LC = 16 << LCI
+
+template <typename C, int NSEC> struct SosCoef { C c[NSEC][5]; };   // b0 b1 b2 -a1 -a2
+
+template <typename C, int NSEC>
+__device__ __forceinline__ C sos_step(const SosCoef<C, NSEC> &k, C (&z)[2 * NSEC], C v)
+{
+#pragma unroll
+    for (int s = 0; s < NSEC; ++s) {
+        C xn = fma(k.c[s][0], v, z[2 * s]);
+        z[2 * s] = fma(k.c[s][1], v, fma(k.c[s][3], xn, z[2 * s + 1]));
+        z[2 * s + 1] = fma(k.c[s][2], v, k.c[s][4] * xn);
+        v = xn;
+    }
+    return v;
+}
+
+__device__ __forceinline__ float  ch_get(const float &v, int)   { return v; }
+__device__ __forceinline__ double ch_get(const double &v, int)  { return v; }
+__device__ __forceinline__ float  ch_get(const float2 &v, int c)  { return c ? v.y : v.x; }
+__device__ __forceinline__ double ch_get(const double2 &v, int c) { return c ? v.y : v.x; }
+__device__ __forceinline__ void ch_set(float &v, int, float x)    { v = x; }
+__device__ __forceinline__ void ch_set(double &v, int, double x)  { v = x; }
+__device__ __forceinline__ void ch_set(float2 &v, int c, float x)   { if (c) v.y = x; else v.x = x; }
+__device__ __forceinline__ void ch_set(double2 &v, int c, double x) { if (c) v.y = x; else v.x = x; }
+
+// e <- e + P * o with P block-lower-triangular (section i never depends on a later section)
+template <typename C, int D>
+__device__ __forceinline__ void matvec_acc(C (&e)[D], const C *__restrict__ P, const C (&o)[D])
+{
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        C acc = e[i];
+#pragma unroll
+        for (int k = 0; k <= (i | 1); ++k) acc = fma(P[i * D + k], o[k], acc);
+        e[i] = acc;
+    }
+}
+
+// Inclusive Kogge-Stone scan of the per-thread carries of ONE channel:
+//   e_t <- sum_{u<=t} A^(LC*(t-u)) e_u .  mats = [SOS_LEVELS][D*D] in shared memory,
+//   xch = SOS_NT*D scratch in shared memory.
+template <typename C, int D>
+__device__ void scan_carries(C (&e)[D], const C *mats, C *xch, int tid)
+{
+    const int lane = tid & 31;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const int off = 1 << j;
+        C o[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) o[d] = __shfl_up_sync(0xffffffffu, e[d], off);
+        if (lane >= off) matvec_acc<C, D>(e, mats + j * D * D, o);
+    }
+    for (int j = 5; j < SOS_LEVELS; ++j) {
+        const int off = 1 << j;
+        __syncthreads();
+#pragma unroll
+        for (int d = 0; d < D; ++d) xch[d * SOS_NT + tid] = e[d];
+        __syncthreads();
+        if (tid >= off) {
+            C o[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) o[d] = xch[d * SOS_NT + tid - off];
+            matvec_acc<C, D>(e, mats + j * D * D, o);
+        }
+    }
+}
+
+template <typename S, int NSEC>
+struct SosArgs {
+    using C = typename Sample<S>::C;
+    const S *x;
+    S *y;
+    int64_t n_in;        // samples readable from x
+    int64_t n_rate;      // samples at the filter rate (n_in * L)
+    int64_t n_out;       // samples written to y (n_rate / M)
+    int32_t L, M;
+    const C *mats;       // [SOS_LEVELS][D*D] device, A^(LC*2^j)
+    C *aggr;             // [tiles][NCH][D]   tile carries (zero tile-start state)
+    C *start;            // [tiles][NCH][D]   true state at tile start (from K2)
+    C *carry;            // [tiles][NCH][D][SOS_NT] chunk carries
+    C *zf;               // final state out [s][2][ch] or NULL
+    int32_t d_real;      // 2 * (sections that are not identity padding)
+    SosCoef<C, NSEC> k;
+};
+
+template <typename S, int LC>
+__device__ __forceinline__ int tile_addr(int v) { return (v & (LC - 1)) * (SOS_NT + 1) + (v / LC); }
+
+template <typename S, int NSEC>
+__device__ void sos_load_tile(S *tile, const SosArgs<S, NSEC> &a, int64_t tile0, int tid)
+{
+    using C = typename Sample<S>::C;
+    constexpr int LC = SosCfg<S>::LC;
+    constexpr int T = SOS_NT * LC;
+    if (a.L == 1) {
+        for (int v = tid; v < T; v += SOS_NT) {
+            int64_t g = tile0 + v;
+            S val = zero_of(S());
+            if (g < a.n_rate) val = a.x[g];
+            tile[tile_addr<S, LC>(v)] = val;
+        }
+    } else {
+        const int L = a.L;
+        int64_t g0 = tile0 + tid;
+        int64_t q = g0 / L;
+        int r = (int)(g0 - q * L);
+        const int dq = SOS_NT / L, dr = SOS_NT - dq * L;
+        const C gain = (C)L;
+        for (int v = tid; v < T; v += SOS_NT) {
+            S val = zero_of(S());
+            if (r == 0 && q < a.n_in) val = scale_of(a.x[q], gain);
+            tile[tile_addr<S, LC>(v)] = val;
+            q += dq;
+            r += dr;
+            if (r >= L) { r -= L; ++q; }
+        }
+    }
+}
+
+template <typename S, int NSEC>
+__global__ void __launch_bounds__(SOS_NT) sos_pass1_kernel(const SosArgs<S, NSEC> a)
+{
+    using C = typename Sample<S>::C;
+    constexpr int NCH = Sample<S>::NCH;
+    constexpr int D = 2 * NSEC;
+    constexpr int LC = SosCfg<S>::LC;
+    constexpr int T = SOS_NT * LC;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    S *tile = reinterpret_cast<S *>(smem_raw);
+    C *mats = reinterpret_cast<C *>(smem_raw + sizeof(S) * (size_t)LC * (SOS_NT + 1));
+    C *xch = reinterpret_cast<C *>(smem_raw);      // aliases the tile (dead after the chunk pass)
+    const int tid = threadIdx.x;
+    const int64_t tile0 = (int64_t)blockIdx.x * T;
+
+    for (int i = tid; i < SOS_LEVELS * D * D; i += SOS_NT) mats[i] = a.mats[i];
+    sos_load_tile<S, NSEC>(tile, a, tile0, tid);
+    __syncthreads();
+
+    C z[NCH][D];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+        for (int d = 0; d < D; ++d) z[c][d] = (C)0;
+#pragma unroll 4
+    for (int n = 0; n < LC; ++n) {
+        S v = tile[n * (SOS_NT + 1) + tid];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) sos_step<C, NSEC>(a.k, z[c], ch_get(v, c));
+    }
+    // chunk carries -> workspace (coalesced over tid)
+    C *cw = a.carry + (size_t)blockIdx.x * NCH * D * SOS_NT;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+        for (int d = 0; d < D; ++d) cw[(c * D + d) * SOS_NT + tid] = z[c][d];
+    // tile carry = last element of the inclusive scan
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        scan_carries<C, D>(z[c], mats, xch, tid);
+        if (tid == SOS_NT - 1) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) a.aggr[((size_t)blockIdx.x * NCH + c) * D + d] = z[c][d];
+        }
+    }
+}
+
+template <typename S, int NSEC>
+__global__ void __launch_bounds__(SOS_NT) sos_pass2_kernel(const SosArgs<S, NSEC> a)
+{
+    using C = typename Sample<S>::C;
+    constexpr int NCH = Sample<S>::NCH;
+    constexpr int D = 2 * NSEC;
+    constexpr int LC = SosCfg<S>::LC;
+    constexpr int T = SOS_NT * LC;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    S *tile = reinterpret_cast<S *>(smem_raw);
+    C *mats = reinterpret_cast<C *>(smem_raw + sizeof(S) * (size_t)LC * (SOS_NT + 1));
+    C *xch = mats + SOS_LEVELS * D * D;
+    const int tid = threadIdx.x;
+    const int64_t tile0 = (int64_t)blockIdx.x * T;
+
+    for (int i = tid; i < SOS_LEVELS * D * D; i += SOS_NT) mats[i] = a.mats[i];
+    sos_load_tile<S, NSEC>(tile, a, tile0, tid);
+
+    C z[NCH][D];
+    const C *cw = a.carry + (size_t)blockIdx.x * NCH * D * SOS_NT;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+        for (int d = 0; d < D; ++d) z[c][d] = cw[(c * D + d) * SOS_NT + tid];
+    __syncthreads();
+
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        C s0[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) s0[d] = a.start[((size_t)blockIdx.x * NCH + c) * D + d];
+        if (tid == 0) matvec_acc<C, D>(z[c], mats, s0);       // fold the tile's true start state
+        scan_carries<C, D>(z[c], mats, xch, tid);             // z = state at END of chunk tid
+        __syncthreads();
+#pragma unroll
+        for (int d = 0; d < D; ++d) xch[d * SOS_NT + tid] = z[c][d];
+        __syncthreads();
+#pragma unroll
+        for (int d = 0; d < D; ++d) z[c][d] = (tid == 0) ? s0[d] : xch[d * SOS_NT + tid - 1];
+    }
+
+    // corrected pass: true start state -> outputs, in place in the tile
+    const int64_t last = a.n_rate - 1 - tile0 - (int64_t)tid * LC;    // position of the final sample
+#pragma unroll 4
+    for (int n = 0; n < LC; ++n) {
+        S v = tile[n * (SOS_NT + 1) + tid];
+        S o;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) ch_set(o, c, sos_step<C, NSEC>(a.k, z[c], ch_get(v, c)));
+        tile[n * (SOS_NT + 1) + tid] = o;
+        if (a.zf != nullptr && n == last) {
+#pragma unroll
+            for (int c = 0; c < NCH; ++c)
+#pragma unroll
+                for (int d = 0; d < D; ++d)
+                    if (d < a.d_real) a.zf[d * NCH + c] = z[c][d];
+        }
+    }
+    __syncthreads();
+    if (a.M == 1) {
+        for (int v = tid; v < T; v += SOS_NT) {
+            int64_t g = tile0 + v;
+            if (g < a.n_out) a.y[g] = tile[tile_addr<S, LC>(v)];
+        }
+    } else {
+        const int M = a.M;
+        int64_t o = (tile0 + M - 1) / M + tid;
+        for (;; o += SOS_NT) {
+            int64_t g = o * M;
+            if (g >= tile0 + T || o >= a.n_out) break;
+            a.y[o] = tile[tile_addr<S, LC>((int)(g - tile0))];
+        }
+    }
+}
+
+// ---- K2: scan of tile carries -----------------------------------------------------------
+template <int D> struct TileScanMats { double m1[D * D]; double pj[SOS_K2_LEVELS][D * D]; };
+
+template <int D>
+__device__ __forceinline__ void matvec_full(double (&out)[D], const double *P, const double (&in)[D])
+{
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) acc = fma(P[i * D + k], in[k], acc);
+        out[i] = acc;
+    }
+}
+
+template <typename C, int D>
+__global__ void __launch_bounds__(SOS_K2_NT)
+sos_tile_scan_kernel(const C *__restrict__ aggr, C *__restrict__ start, const C *__restrict__ zi,
+                     int64_t n_tiles, int64_t run, int nch, int d_real, const TileScanMats<D> mm)
+{
+    extern __shared__ double xchd[];             // [D][SOS_K2_NT]
+    const int tid = threadIdx.x;
+    const int64_t t0 = (int64_t)tid * run;
+    const int64_t t1 = (t0 + run < n_tiles) ? t0 + run : n_tiles;
+    for (int c = 0; c < nch; ++c) {
+        double s[D], e[D], tmp[D];
+        // initial state of the whole stream (scipy zi layout [s][2][ch] == [d][ch])
+#pragma unroll
+        for (int d = 0; d < D; ++d) s[d] = (zi != nullptr && d < d_real) ? (double)zi[d * nch + c] : 0.0;
+        // local run carry (zero start, except run 0 which starts from zi)
+#pragma unroll
+        for (int d = 0; d < D; ++d) e[d] = (tid == 0) ? s[d] : 0.0;
+        for (int64_t k = t0; k < t1; ++k) {
+            matvec_full<D>(tmp, mm.m1, e);
+#pragma unroll
+            for (int d = 0; d < D; ++d) e[d] = tmp[d] + (double)aggr[(k * nch + c) * D + d];
+        }
+        // Kogge-Stone over runs
+        for (int j = 0; j < SOS_K2_LEVELS; ++j) {
+            const int off = 1 << j;
+            __syncthreads();
+#pragma unroll
+            for (int d = 0; d < D; ++d) xchd[d * SOS_K2_NT + tid] = e[d];
+            __syncthreads();
+            if (tid >= off) {
+                double o[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) o[d] = xchd[d * SOS_K2_NT + tid - off];
+                matvec_full<D>(tmp, mm.pj[j], o);
+#pragma unroll
+                for (int d = 0; d < D; ++d) e[d] += tmp[d];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int d = 0; d < D; ++d) xchd[d * SOS_K2_NT + tid] = e[d];
+        __syncthreads();
+        if (tid > 0) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) s[d] = xchd[d * SOS_K2_NT + tid - 1];
+        }
+        for (int64_t k = t0; k < t1; ++k) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) start[(k * nch + c) * D + d] = (C)s[d];
+            matvec_full<D>(tmp, mm.m1, s);
+#pragma unroll
+            for (int d = 0; d < D; ++d) s[d] = tmp[d] + (double)aggr[(k * nch + c) * D + d];
+        }
+        __syncthreads();
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------
+struct SosGroup {
+    int nsec;                          // sections in this launch group incl. identity padding (1,2,4,6,8)
+    int nsec_real;                     // sections that came from the user's sos
+    double coef[SOS_MAXSEC][5];        // b0 b1 b2 -a1 -a2
+    std::vector<double> A;             // D x D one-sample state transition
+    std::vector<double> tileA[3];      // A^(512*LC) for LC = 16,32,64
+    float *mats_f32[3];                // device [SOS_LEVELS][D*D], per LC
+    double *mats_f64[3];
+};
+
+struct b200dsp_sos_plan_impl {
+    int nsec;
+    std::vector<SosGroup> groups;
+};
+
+static void matmul(const std::vector<double> &a, const std::vector<double> &b, std::vector<double> &c, int D)
+{
+    std::vector<double> r((size_t)D * D, 0.0);
+    for (int i = 0; i < D; ++i)
+        for (int k = 0; k < D; ++k) {
+            double aik = a[i * D + k];
+            if (aik == 0.0) continue;
+            for (int j = 0; j < D; ++j) r[i * D + j] += aik * b[k * D + j];
+        }
+    c.swap(r);
+}
+
+static void matpow(const std::vector<double> &a, int64_t p, std::vector<double> &out, int D)
+{
+    std::vector<double> res((size_t)D * D, 0.0), base = a;
+    for (int i = 0; i < D; ++i) res[i * D + i] = 1.0;
+    while (p > 0) {
+        if (p & 1) matmul(res, base, res, D);
+        p >>= 1;
+        if (p) matmul(base, base, base, D);
+    }
+    out.swap(res);
+}
+
+template <typename S, int NSEC>
+static int run_group(const SosGroup &g, const S *x, S *y, int64_t n_in, int64_t n_rate, int64_t n_out,
+                     int32_t L, int32_t M, const void *zi, void *zf, unsigned char *ws,
+                     cudaStream_t stream)
+{
+    using C = typename Sample<S>::C;
+    constexpr int NCH = Sample<S>::NCH;
+    constexpr int D = 2 * NSEC;
+    constexpr int LC = SosCfg<S>::LC;
+    constexpr int LCI = SosCfg<S>::LCI;
+    constexpr int64_t T = (int64_t)SOS_NT * LC;
+    const int64_t n_tiles = (n_rate + T - 1) / T;
+    if (n_tiles > 2147483647LL) {
+        set_error("sos: too many tiles");
+        return B200DSP_E_UNSUPPORTED;
+    }
+    SosArgs<S, NSEC> a;
+    a.x = x;
+    a.y = y;
+    a.n_in = n_in;
+    a.n_rate = n_rate;
+    a.n_out = n_out;
+    a.L = L;
+    a.M = M;
+    a.mats = sizeof(C) == 4 ? reinterpret_cast<const C *>(g.mats_f32[LCI])
+                            : reinterpret_cast<const C *>(g.mats_f64[LCI]);
+    size_t per_tile = (size_t)NCH * D * sizeof(C);
+    size_t off = 0;
+    a.aggr = reinterpret_cast<C *>(ws + off);
+    off += ((size_t)n_tiles * per_tile + 255) & ~(size_t)255;
+    a.start = reinterpret_cast<C *>(ws + off);
+    off += ((size_t)n_tiles * per_tile + 255) & ~(size_t)255;
+    a.carry = reinterpret_cast<C *>(ws + off);
+    a.zf = static_cast<C *>(zf);
+    a.d_real = 2 * g.nsec_real;
+    for (int s = 0; s < NSEC; ++s)
+        for (int q = 0; q < 5; ++q) a.k.c[s][q] = (C)g.coef[s][q];
+
+    const size_t tile_bytes = sizeof(S) * (size_t)LC * (SOS_NT + 1);
+    const size_t mats_bytes = sizeof(C) * (size_t)SOS_LEVELS * D * D;
+    const size_t xch_bytes = sizeof(C) * (size_t)SOS_NT * D;
+    size_t smem1 = tile_bytes + mats_bytes;
+    if (smem1 < xch_bytes) smem1 = xch_bytes;          // xch aliases the tile in K1
+    size_t smem3 = tile_bytes + mats_bytes + xch_bytes;
+    if (smem3 > kMaxSmemPerBlock) {
+        set_error("sos: shared-memory budget exceeded (%zu B)", smem3);
+        return B200DSP_E_UNSUPPORTED;
+    }
+    auto k1 = sos_pass1_kernel<S, NSEC>;
+    auto k3 = sos_pass2_kernel<S, NSEC>;
+    B200_CHECK_CUDA(allow_smem(k1, smem1));
+    B200_CHECK_CUDA(allow_smem(k3, smem3));
+
+    k1<<<(unsigned)n_tiles, SOS_NT, smem1, stream>>>(a);
+    B200_CHECK_LAUNCH("sos_pass1_kernel");
+
+    // tile-level scan matrices: m1 = A^T, pj = (A^T)^(run*2^j)
+    TileScanMats<D> mm;
+    const int64_t run = (n_tiles + SOS_K2_NT - 1) / SOS_K2_NT;
+    memcpy(mm.m1, g.tileA[LCI].data(), sizeof(double) * D * D);
+    std::vector<double> p;
+    matpow(g.tileA[LCI], run, p, D);
+    for (int j = 0; j < SOS_K2_LEVELS; ++j) {
+        memcpy(mm.pj[j], p.data(), sizeof(double) * D * D);
+        if (j + 1 < SOS_K2_LEVELS) matmul(p, p, p, D);
+    }
+    auto k2 = sos_tile_scan_kernel<C, D>;
+    size_t smem2 = sizeof(double) * (size_t)D * SOS_K2_NT;
+    k2<<<1, SOS_K2_NT, smem2, stream>>>(a.aggr, a.start, static_cast<const C *>(zi), n_tiles, run, NCH, a.d_real, mm);
+    B200_CHECK_LAUNCH("sos_tile_scan_kernel");
+
+    k3<<<(unsigned)n_tiles, SOS_NT, smem3, stream>>>(a);
+    B200_CHECK_LAUNCH("sos_pass2_kernel");
+    return B200DSP_OK;
+}
+
+template <typename S>
+static int run_group_nsec(const SosGroup &g, const S *x, S *y, int64_t n_in, int64_t n_rate,
+                          int64_t n_out, int32_t L, int32_t M, const void *zi, void *zf,
+                          unsigned char *ws, cudaStream_t st)
+{
+    switch (g.nsec) {
+    case 1: return run_group<S, 1>(g, x, y, n_in, n_rate, n_out, L, M, zi, zf, ws, st);
+    case 2: return run_group<S, 2>(g, x, y, n_in, n_rate, n_out, L, M, zi, zf, ws, st);
+    case 4: return run_group<S, 4>(g, x, y, n_in, n_rate, n_out, L, M, zi, zf, ws, st);
+    case 6: return run_group<S, 6>(g, x, y, n_in, n_rate, n_out, L, M, zi, zf, ws, st);
+    case 8: return run_group<S, 8>(g, x, y, n_in, n_rate, n_out, L, M, zi, zf, ws, st);
+    }
+    set_error("sos: bad group size %d", g.nsec);
+    return B200DSP_E_BADARG;
+}
+
+static size_t dtype_size(int dtype)
+{
+    switch (dtype) {
+    case B200DSP_F32: return 4;
+    case B200DSP_F64: return 8;
+    case B200DSP_C64: return 8;
+    case B200DSP_C128: return 16;
+    }
+    return 0;
+}
+
+// workspace = [scan area (aggr, start, carry) for the largest group] [tmp stream if >1 group]
+static size_t sos_scan_area_bytes(int dtype, int64_t n_rate)
+{
+    const int lc = dtype == B200DSP_F32 ? 64 : (dtype == B200DSP_C128 ? 16 : 32);
+    const int nch = (dtype == B200DSP_C64 || dtype == B200DSP_C128) ? 2 : 1;
+    const size_t csz = (dtype == B200DSP_F32 || dtype == B200DSP_C64) ? 4 : 8;
+    const int64_t T = (int64_t)SOS_NT * lc;
+    const int64_t n_tiles = (n_rate + T - 1) / T;
+    const size_t per_tile = (size_t)nch * 2 * SOS_MAXSEC * csz;
+    size_t a = ((size_t)n_tiles * per_tile + 255) & ~(size_t)255;
+    return 2 * a + (size_t)n_tiles * per_tile * SOS_NT + 256;
+}
+
+template <typename S>
+static int sos_run(const b200dsp_sos_plan_impl *p, const S *x, S *y, int64_t n, int32_t L, int32_t M,
+                   const void *zi, void *zf, unsigned char *ws, int dtype, cudaStream_t st)
+{
+    using C = typename Sample<S>::C;
+    constexpr int NCH = Sample<S>::NCH;
+    const int64_t n_rate = n * L;
+    const int64_t n_out = n_rate / M;
+    const size_t ng = p->groups.size();
+    S *tmp = nullptr;
+    if (ng > 1) tmp = reinterpret_cast<S *>(ws + ((sos_scan_area_bytes(dtype, n_rate) + 255) & ~(size_t)255));
+    size_t sec0 = 0;
+    for (size_t gi = 0; gi < ng; ++gi) {
+        const SosGroup &g = p->groups[gi];
+        const bool first = gi == 0, last = gi + 1 == ng;
+        const S *src = first ? x : tmp;
+        S *dst = last ? y : tmp;
+        const C *zig = zi ? static_cast<const C *>(zi) + sec0 * 2 * NCH : nullptr;
+        C *zfg = zf ? static_cast<C *>(zf) + sec0 * 2 * NCH : nullptr;
+        int rc = run_group_nsec<S>(g, src, dst, first ? n : n_rate, n_rate, last ? n_out : n_rate,
+                                   first ? L : 1, last ? M : 1, zig, zfg, ws, st);
+        if (rc != B200DSP_OK) return rc;
+        sec0 += g.nsec_real;
+    }
+    return B200DSP_OK;
+}
+
+}  // namespace b200dsp
+
+using namespace b200dsp;
+
+struct b200dsp_sos_plan : b200dsp_sos_plan_impl {};
+
+extern "C" {
+
+int b200dsp_sos_plan_create(const double *sos_host, int32_t nsec, b200dsp_sos_plan **plan)
+{
+    if (!sos_host || !plan || nsec < 1) {
+        set_error("sos_plan_create: bad argument (nsec=%d)", nsec);
+        return B200DSP_E_BADARG;
+    }
+    for (int s = 0; s < nsec; ++s)
+        if (sos_host[6 * s + 3] != 1.0) {
+            set_error("sos_plan_create: sos[%d][3] must be 1 (scipy _validate_sos)", s);
+            return B200DSP_E_BADARG;
+        }
+    b200dsp_sos_plan *p = new b200dsp_sos_plan();
+    p->nsec = nsec;
+    for (int s0 = 0; s0 < nsec; s0 += SOS_MAXSEC) {
+        SosGroup g;
+        g.nsec_real = (nsec - s0 < SOS_MAXSEC) ? nsec - s0 : SOS_MAXSEC;
+        // kernels are instantiated for 1,2,4,6,8 sections; odd counts get an identity section
+        // (b0 = 1, everything else 0: x_new = x, both states stay 0 -- exact)
+        g.nsec = (g.nsec_real == 1) ? 1 : ((g.nsec_real + 1) & ~1);
+        const int D = 2 * g.nsec;
+        static const double ident[6] = {1.0, 0.0, 0.0, 1.0, 0.0, 0.0};
+        for (int s = 0; s < g.nsec; ++s) {
+            const double *q = (s < g.nsec_real) ? sos_host + 6 * (s0 + s) : ident;
+            g.coef[s][0] = q[0];
+            g.coef[s][1] = q[1];
+            g.coef[s][2] = q[2];
+            g.coef[s][3] = -q[4];
+            g.coef[s][4] = -q[5];
+        }
+        // one-sample zero-input state transition: column d = next state from unit state e_d
+        g.A.assign((size_t)D * D, 0.0);
+        for (int d = 0; d < D; ++d) {
+            std::vector<double> z(D, 0.0);
+            z[d] = 1.0;
+            double v = 0.0;
+            for (int s = 0; s < g.nsec; ++s) {
+                double xn = g.coef[s][0] * v + z[2 * s];
+                double z0 = g.coef[s][1] * v + g.coef[s][3] * xn + z[2 * s + 1];
+                double z1 = g.coef[s][2] * v + g.coef[s][4] * xn;
+                z[2 * s] = z0;
+                z[2 * s + 1] = z1;
+                v = xn;
+            }
+            for (int i = 0; i < D; ++i) g.A[i * D + d] = z[i];
+        }
+        for (int li = 0; li < 3; ++li) {
+            g.mats_f32[li] = nullptr;
+            g.mats_f64[li] = nullptr;
+        }
+        cudaError_t e = cudaSuccess;
+        for (int li = 0; li < 3 && e == cudaSuccess; ++li) {
+            const int lc = 16 << li;
+            std::vector<double> pw;
+            matpow(g.A, lc, pw, D);
+            std::vector<double> all((size_t)SOS_LEVELS * D * D);
+            for (int j = 0; j < SOS_LEVELS; ++j) {
+                memcpy(all.data() + (size_t)j * D * D, pw.data(), sizeof(double) * D * D);
+                matmul(pw, pw, pw, D);
+            }
+            g.tileA[li] = pw;       // A^(lc * 512)
+            std::vector<float> allf(all.begin(), all.end());
+            e = cudaMalloc(&g.mats_f32[li], allf.size() * sizeof(float));
+            if (e == cudaSuccess) e = cudaMalloc(&g.mats_f64[li], all.size() * sizeof(double));
+            if (e == cudaSuccess) e = cudaMemcpy(g.mats_f32[li], allf.data(), allf.size() * sizeof(float), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(g.mats_f64[li], all.data(), all.size() * sizeof(double), cudaMemcpyHostToDevice);
+        }
+        p->groups.push_back(g);
+        if (e != cudaSuccess) {
+            set_error("sos_plan_create: %s", cudaGetErrorString(e));
+            b200dsp_sos_plan_destroy(p);
+            return B200DSP_E_CUDA;
+        }
+    }
+    *plan = p;
+    return B200DSP_OK;
+}
+
+void b200dsp_sos_plan_destroy(b200dsp_sos_plan *plan)
+{
+    if (!plan) return;
+    for (auto &g : plan->groups)
+        for (int li = 0; li < 3; ++li) {
+            cudaFree(g.mats_f32[li]);
+            cudaFree(g.mats_f64[li]);
+        }
+    delete plan;
+}
+
+int32_t b200dsp_sos_plan_nsec(const b200dsp_sos_plan *plan) { return plan ? plan->nsec : 0; }
+
+size_t b200dsp_sos_workspace_bytes(const b200dsp_sos_plan *plan, int dtype, int64_t n, int32_t L)
+{
+    if (!plan || n < 0 || L < 1 || dtype_size(dtype) == 0) return 0;
+    const int64_t n_rate = n * L;
+    size_t b = (sos_scan_area_bytes(dtype, n_rate) + 255) & ~(size_t)255;
+    if (plan->groups.size() > 1) b += (size_t)n_rate * dtype_size(dtype) + 256;
+    return b;
+}
+
+int b200dsp_sos_filter(const b200dsp_sos_plan *plan, int dtype, const void *x, void *y, int64_t n,
+                       int32_t L, int32_t M, const void *zi, void *zf, void *ws, size_t ws_bytes,
+                       void *stream)
+{
+    if (!plan || n < 0 || L < 1 || M < 1 || (L > 1 && M > 1) || (n > 0 && (!x || !y))) {
+        set_error("sos_filter: bad argument (L=%d, M=%d)", L, M);
+        return B200DSP_E_BADARG;
+    }
+    if (dtype_size(dtype) == 0) {
+        set_error("sos_filter: bad dtype code %d", dtype);
+        return B200DSP_E_DTYPE;
+    }
+    if (n == 0) return B200DSP_OK;
+    if (!ws || ws_bytes < b200dsp_sos_workspace_bytes(plan, dtype, n, L)) {
+        set_error("sos_filter: workspace too small (%zu < %zu)", ws_bytes,
+                  b200dsp_sos_workspace_bytes(plan, dtype, n, L));
+        return B200DSP_E_WORKSPACE;
+    }
+    unsigned char *w = static_cast<unsigned char *>(ws);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+    case B200DSP_F32: return sos_run<float>(plan, (const float *)x, (float *)y, n, L, M, zi, zf, w, dtype, st);
+    case B200DSP_F64: return sos_run<double>(plan, (const double *)x, (double *)y, n, L, M, zi, zf, w, dtype, st);
+    case B200DSP_C64: return sos_run<float2>(plan, (const float2 *)x, (float2 *)y, n, L, M, zi, zf, w, dtype, st);
+    case B200DSP_C128: return sos_run<double2>(plan, (const double2 *)x, (double2 *)y, n, L, M, zi, zf, w, dtype, st);
+    }
+    return B200DSP_E_DTYPE;
+}
+
+}  // extern "C"

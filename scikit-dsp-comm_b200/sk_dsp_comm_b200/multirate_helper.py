@@ -1,0 +1,219 @@
+"""B200 drop-in for ``sk_dsp_comm.multirate_helper`` (reference:
+src/sk_dsp_comm/multirate_helper.py:85-208).
+
+``multirate_FIR`` / ``multirate_IIR`` keep the reference's constructor, attributes
+(``b``, ``sos``, ``N_forder``), method names, keyword names and defaults
+(``L_change=12``, ``M_change=12``) and its two ``log.info`` lines, so notebooks written against
+the reference run unchanged:
+
+    import sk_dsp_comm_b200.multirate_helper as mrh
+    y = mrh.multirate_FIR(b).filter(x)
+
+The arithmetic (``scipy.signal.lfilter`` / ``sosfilt`` in the reference) runs in hand-written
+sm_100a CUDA kernels through the ctypes C ABI (``include/b200dsp.h``); see ``_io.py`` for the
+container / dtype rules.  Plot helpers (``freq_resp``, ``zplane``) are out of scope
+ and raise ``NotImplementedError``.
+"""
+from __future__ import annotations
+
+from logging import getLogger
+
+import numpy as np
+import torch
+
+from . import _engine
+from ._io import Staged
+
+log = getLogger(__name__)
+
+# inputs at least this long that live on the HOST go through the chunked, copy/compute
+# overlapped pipeline in hostpipe.py instead of one monolithic H2D -> kernel -> D2H
+_HOST_PIPE_MIN = 1 << 22
+
+
+def _rows(t: torch.Tensor):
+    """lfilter/sosfilt filter along the last axis of an N-D input."""
+    if t.dim() == 1:
+        return [t.contiguous()], None
+    shape = t.shape
+    flat = t.reshape(-1, shape[-1]).contiguous()
+    return [flat[i] for i in range(flat.shape[0])], shape
+
+
+def _require_1d(x, what):
+    nd = x.dim() if isinstance(x, torch.Tensor) else np.ndim(x)
+    if nd != 1:
+        # the reference reaches sigsys.upsample/downsample, whose reshape rejects N-D input
+        raise ValueError("%s expects a 1-D signal" % what)
+
+
+class multirate_FIR(object):
+    """
+    A simple class for encapsulating FIR filtering, or FIR upsample/
+    filter, or FIR filter/downsample operations used in modeling a comm
+    system. Objects of this class will hold the required filter
+    coefficients once an object is instantiated.
+
+    B200-native re-implementation of the reference class of the same name
+    (multirate_helper.py:85-143).
+    """
+
+    def __init__(self, b):
+        """
+        Object constructor method
+        """
+        self.N_forder = len(b)
+        self.b = b
+        log.info('FIR filter taps = %d' % self.N_forder)
+        barr = np.asarray(b)
+        if barr.ndim != 1 or barr.size == 0:
+            # scipy.signal.lfilter: "object of too small depth" / empty numerator
+            raise ValueError("numerator b must be a non-empty 1-D sequence of taps")
+        if barr.dtype.kind == "c":
+            raise NotImplementedError("complex FIR taps are not supported by the B200 engine")
+        self._plan = _engine.FirPlan(barr.astype(np.float64))
+
+    # -- reference: y = signal.lfilter(self.b,[1],x)  (multirate_helper.py:104-109)
+    def filter(self, x):
+        """
+        Filter the signal
+        """
+        if isinstance(x, torch.Tensor) and not x.is_cuda and x.dim() == 1 \
+                and x.numel() >= _HOST_PIPE_MIN and x.dtype in _engine.DTYPE_CODE:
+            from . import hostpipe
+            return hostpipe.fir_filter_host(self._plan, x)
+        st = Staged(x)
+        rows, shape = _rows(st.tensor)
+        outs = [_engine.fir_filter(self._plan, r) if r.numel() else r.clone() for r in rows]
+        y = outs[0] if shape is None else torch.stack(outs).reshape(shape)
+        return st.finish(y)
+
+    # -- reference: y = L*upsample(x,L); y = lfilter(b,[1],y)  (multirate_helper.py:112-118)
+    def up(self, x, L_change=12):
+        """
+        Upsample and filter the signal
+        """
+        _require_1d(x, "up")
+        L = int(L_change - 1) + 1        # sigsys.upsample truncates float factors: int(L-1) zeros
+        if L < 1:
+            raise ValueError("negative dimensions are not allowed")
+        st = Staged(x)
+        t = st.tensor.contiguous()
+        if t.numel() == 0:
+            return st.finish(t.clone())
+        y = _engine.fir_up(self._plan, t, L)
+        if L != L_change:
+            y = y * (float(L_change) / L)     # reference gain is the un-truncated L_change
+        return st.finish(y)
+
+    # -- reference: y = lfilter(b,[1],x); y = downsample(y,M)  (multirate_helper.py:121-127)
+    def dn(self, x, M_change=12):
+        """
+        Downsample and filter the signal
+        """
+        if not isinstance(M_change, int):
+            raise TypeError("M must be an int")
+        _require_1d(x, "dn")
+        st = Staged(x)
+        t = st.tensor.contiguous()
+        if t.numel() // M_change == 0:
+            return st.finish(torch.empty(0, dtype=t.dtype, device=t.device))
+        return st.finish(_engine.fir_dn(self._plan, t, M_change))
+
+    def freq_resp(self, mode='dB', fs=8000, ylim=[-100, 2]):
+        raise NotImplementedError("plot helpers are out of scope of the B200 engine (SURVEY.md section 2)")
+
+    def zplane(self, auto_scale=True, size=2, detect_mult=True, tol=0.001):
+        raise NotImplementedError("plot helpers are out of scope of the B200 engine (SURVEY.md section 2)")
+
+
+def _validate_sos(sos):
+    """scipy.signal._validate_sos: (n_sections, 6) with sos[:, 3] == 1, else ValueError."""
+    sos = np.atleast_2d(np.asarray(sos))
+    if sos.ndim != 2:
+        raise ValueError('sos array must be 2D')
+    n_sections, m = sos.shape
+    if m != 6:
+        raise ValueError('sos array must be shape (n_sections, 6)')
+    if not (sos[:, 3] == 1).all():
+        raise ValueError('sos[:, 3] should be all ones')
+    return sos
+
+
+class multirate_IIR(object):
+    """
+    A simple class for encapsulating IIR filtering, or IIR upsample/
+    filter, or IIR filter/downsample operations used in modeling a comm
+    system. All filtering is done on a cascade of second-order sections,
+    y = sosfilt(sos,x).
+
+    B200-native re-implementation of the reference class of the same name
+    (multirate_helper.py:146-208): the cascade runs as a parallel-prefix recurrence
+    (csrc/sos_scan.cu).
+    """
+
+    def __init__(self, sos):
+        """
+        Object constructor method
+        """
+        self.N_forder = np.sum(np.sign(np.abs(sos[:, 2]))) \
+                      + np.sum(np.sign(np.abs(sos[:, 1])))
+        self.sos = sos
+        log.info('IIR filter order = %d' % self.N_forder)
+        self._plan = None
+
+    def _get_plan(self):
+        if self._plan is None:
+            sos = _validate_sos(self.sos)          # sosfilt validates at call time in the reference
+            if sos.dtype.kind == "c":
+                raise NotImplementedError("complex sos coefficients are not supported by the B200 engine")
+            self._plan = _engine.SosPlan(sos.astype(np.float64))
+        return self._plan
+
+    # -- reference: y = signal.sosfilt(self.sos,x)  (multirate_helper.py:169-174)
+    def filter(self, x):
+        """
+        Filter the signal using second-order sections
+        """
+        plan = self._get_plan()
+        st = Staged(x)
+        rows, shape = _rows(st.tensor)
+        outs = [_engine.sos_filter(plan, r) for r in rows]
+        y = outs[0] if shape is None else torch.stack(outs).reshape(shape)
+        return st.finish(y)
+
+    # -- reference: y = L*upsample(x,L); y = sosfilt(sos,y)  (multirate_helper.py:177-183)
+    def up(self, x, L_change=12):
+        """
+        Upsample and filter the signal
+        """
+        plan = self._get_plan()
+        _require_1d(x, "up")
+        L = int(L_change - 1) + 1
+        if L < 1:
+            raise ValueError("negative dimensions are not allowed")
+        st = Staged(x)
+        t = st.tensor.contiguous()
+        y = _engine.sos_filter(plan, t, L=L)
+        if L != L_change:
+            y = y * (float(L_change) / L)
+        return st.finish(y)
+
+    # -- reference: y = sosfilt(sos,x); y = downsample(y,M)  (multirate_helper.py:186-192)
+    def dn(self, x, M_change=12):
+        """
+        Downsample and filter the signal
+        """
+        if not isinstance(M_change, int):
+            raise TypeError("M must be an int")
+        plan = self._get_plan()
+        _require_1d(x, "dn")
+        st = Staged(x)
+        t = st.tensor.contiguous()
+        return st.finish(_engine.sos_filter(plan, t, M=M_change))
+
+    def freq_resp(self, mode='dB', fs=8000, ylim=[-100, 2]):
+        raise NotImplementedError("plot helpers are out of scope of the B200 engine (SURVEY.md section 2)")
+
+    def zplane(self, auto_scale=True, size=2, detect_mult=True, tol=0.001):
+        raise NotImplementedError("plot helpers are out of scope of the B200 engine (SURVEY.md section 2)")
