@@ -287,7 +287,7 @@ class FirCpuBaseline:
         self.cores = cores or len(os.sched_getaffinity(0))
         self.chunk = chunk
         self.b_bytes = np.asarray(b, dtype=np.float64).tobytes()
-        self.pool = mp.get_context("spawn").Pool(self.cores)
+        self.pool = mp.get_context("fork").Pool(self.cores)      # created before any CUDA init
         self.tasks = [(1000 + i, chunk, self.b_bytes) for i in range(self.cores)]
         self.samples_per_pass = self.cores * chunk
         self.run_pass()                                    # generate inputs, warm numpy

@@ -40,7 +40,21 @@ __device__ __forceinline__ int pad_idx(int i) { return i + i / R; }
 
 template <typename C> struct __align__(16) TapVec { C v[16 / sizeof(C)]; };
 
-template <typename S, typename C, int R, int NT>
+// PK: complex64 only -- one packed FFMA2 (fma.rn.f32x2, new on sm_100) per complex MAC.  The
+// (re,im) accumulator and sample pairs are 64-bit register operands, so every FFMA2 reads two
+// full-width operands (acc pair, sample pair; the (t,t) tap pair sits in the operand-reuse
+// cache) -- no even/odd register-bank conflicts, half the issue slots of two scalar FFMAs.
+template <typename S, bool PK> struct MacOp {
+    template <typename C>
+    static __device__ __forceinline__ void run(S &acc, C t, const S &x) { tap_fma(acc, t, x); }
+};
+template <> struct MacOp<float2, true> {
+    static __device__ __forceinline__ void run(float2 &acc, float t, const float2 &x) {
+        acc = __ffma2_rn(make_float2(t, t), x, acc);
+    }
+};
+
+template <typename S, typename C, int R, int NT, bool PK = false>
 __global__ void __launch_bounds__(NT) fir_poly_kernel(const FirArgs<S, C> a)
 {
     constexpr int TILE = NT * R;
@@ -119,7 +133,7 @@ __global__ void __launch_bounds__(NT) fir_poly_kernel(const FirArgs<S, C> a)
                             w[(R - kk) % R] = (kk == 0) ? gp[0] : gp[-1 - kk];
                             const C t = tv.v[u];
 #pragma unroll
-                            for (int j = 0; j < R; ++j) tap_fma(acc[j], t, w[(j - kk + R) % R]);
+                            for (int j = 0; j < R; ++j) MacOp<S, PK>::run(acc[j], t, w[(j - kk + R) % R]);
                         }
                     }
                     gp -= (R + 1);
@@ -151,7 +165,7 @@ struct b200dsp_fir_plan_impl {
 
 static thread_local int g_fir_variant = 0;
 
-template <typename S, int R, int NT>
+template <typename S, int R, int NT, bool PK = false>
 static int launch_fir(const b200dsp_fir_plan_impl *p, const void *x, const void *hist, void *y,
                       int64_t n, int64_t n_m, int32_t L, int32_t M, int32_t hist_len,
                       cudaStream_t stream)
@@ -196,7 +210,7 @@ static int launch_fir(const b200dsp_fir_plan_impl *p, const void *x, const void 
         smem = taps_bytes + xs_bytes + (st_elems + st_elems / R + 1) * sizeof(S);
     }
     if (smem > kMaxSmemPerBlock) return B200DSP_E_UNSUPPORTED;
-    auto kern = fir_poly_kernel<S, C, R, NT>;
+    auto kern = fir_poly_kernel<S, C, R, NT, PK>;
     B200_CHECK_CUDA(allow_smem(kern, smem));
     int64_t tiles = (n_m + TILE - 1) / TILE;
     if (tiles > 2147483647LL) {
@@ -209,23 +223,23 @@ static int launch_fir(const b200dsp_fir_plan_impl *p, const void *x, const void 
 }
 
 // Try progressively smaller tiles until the staging fits in shared memory.
-template <typename S, int R>
+template <typename S, int R, bool PK = false>
 static int launch_fir_fit(const b200dsp_fir_plan_impl *p, const void *x, const void *hist, void *y,
                           int64_t n, int64_t n_m, int32_t L, int32_t M, int32_t hist_len,
                           cudaStream_t stream, int nt_first)
 {
     int rc = B200DSP_E_UNSUPPORTED;
     if (nt_first >= 256) {
-        rc = launch_fir<S, R, 256>(p, x, hist, y, n, n_m, L, M, hist_len, stream);
+        rc = launch_fir<S, R, 256, PK>(p, x, hist, y, n, n_m, L, M, hist_len, stream);
         if (rc != B200DSP_E_UNSUPPORTED) return rc;
     }
     if (nt_first >= 128) {
-        rc = launch_fir<S, R, 128>(p, x, hist, y, n, n_m, L, M, hist_len, stream);
+        rc = launch_fir<S, R, 128, PK>(p, x, hist, y, n, n_m, L, M, hist_len, stream);
         if (rc != B200DSP_E_UNSUPPORTED) return rc;
     }
-    rc = launch_fir<S, R, 64>(p, x, hist, y, n, n_m, L, M, hist_len, stream);
+    rc = launch_fir<S, R, 64, PK>(p, x, hist, y, n, n_m, L, M, hist_len, stream);
     if (rc != B200DSP_E_UNSUPPORTED) return rc;
-    rc = launch_fir<S, R, 32>(p, x, hist, y, n, n_m, L, M, hist_len, stream);
+    rc = launch_fir<S, R, 32, PK>(p, x, hist, y, n, n_m, L, M, hist_len, stream);
     if (rc == B200DSP_E_UNSUPPORTED)
         set_error("fir: filter (%d taps, L=%d, M=%d) too long for on-chip staging", p->ntaps, L, M);
     return rc;
@@ -243,6 +257,9 @@ static int fir_dispatch(const b200dsp_fir_plan_impl *p, int dtype, const void *x
     case B200DSP_C64:
         if (v == 1) return launch_fir_fit<float2, 16>(p, x, hist, y, n, n_m, L, M, hist_len, s, 256);
         if (v == 2) return launch_fir_fit<float2, 16>(p, x, hist, y, n, n_m, L, M, hist_len, s, 128);
+        if (v == 3) return launch_fir_fit<float2, 32, true>(p, x, hist, y, n, n_m, L, M, hist_len, s, 128);
+        if (v == 4) return launch_fir_fit<float2, 16, true>(p, x, hist, y, n, n_m, L, M, hist_len, s, 128);
+        if (v == 5) return launch_fir_fit<float2, 16, true>(p, x, hist, y, n, n_m, L, M, hist_len, s, 256);
         return launch_fir_fit<float2, 32>(p, x, hist, y, n, n_m, L, M, hist_len, s, 128);
     case B200DSP_F64:
         return launch_fir_fit<double, 16>(p, x, hist, y, n, n_m, L, M, hist_len, s, 128);

@@ -83,16 +83,10 @@ __device__ __forceinline__ void matvec_acc(C (&e)[D], const C *__restrict__ P, c
 template <typename C, int D>
 __device__ void scan_carries(C (&e)[D], const C *mats, C *xch, int tid)
 {
-    const int lane = tid & 31;
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-        const int off = 1 << j;
-        C o[D];
-#pragma unroll
-        for (int d = 0; d < D; ++d) o[d] = __shfl_up_sync(0xffffffffu, e[d], off);
-        if (lane >= off) matvec_acc<C, D>(e, mats + j * D * D, o);
-    }
-    for (int j = 5; j < SOS_LEVELS; ++j) {
+    // block-wide Kogge-Stone: every level goes through shared memory because the partner
+    // tid - 2^j lives in the previous warp for the low lanes (a warp-shuffle phase would stop
+    // at the warp boundary and leave the prefix incomplete).
+    for (int j = 0; j < SOS_LEVELS; ++j) {
         const int off = 1 << j;
         __syncthreads();
 #pragma unroll
