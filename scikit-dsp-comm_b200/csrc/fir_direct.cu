@@ -257,10 +257,11 @@ static int fir_dispatch(const b200dsp_fir_plan_impl *p, int dtype, const void *x
     case B200DSP_C64:
         if (v == 1) return launch_fir_fit<float2, 16>(p, x, hist, y, n, n_m, L, M, hist_len, s, 256);
         if (v == 2) return launch_fir_fit<float2, 16>(p, x, hist, y, n, n_m, L, M, hist_len, s, 128);
-        if (v == 3) return launch_fir_fit<float2, 32, true>(p, x, hist, y, n, n_m, L, M, hist_len, s, 128);
+        if (v == 3) return launch_fir_fit<float2, 32>(p, x, hist, y, n, n_m, L, M, hist_len, s, 128);
         if (v == 4) return launch_fir_fit<float2, 16, true>(p, x, hist, y, n, n_m, L, M, hist_len, s, 128);
         if (v == 5) return launch_fir_fit<float2, 16, true>(p, x, hist, y, n, n_m, L, M, hist_len, s, 256);
-        return launch_fir_fit<float2, 32>(p, x, hist, y, n, n_m, L, M, hist_len, s, 128);
+        // default: 32 outputs/thread, packed FFMA2 (fastest CUDA-core variant measured on B200)
+        return launch_fir_fit<float2, 32, true>(p, x, hist, y, n, n_m, L, M, hist_len, s, 128);
     case B200DSP_F64:
         return launch_fir_fit<double, 16>(p, x, hist, y, n, n_m, L, M, hist_len, s, 128);
     case B200DSP_C128:

@@ -6,9 +6,38 @@
 
 namespace b200dsp {
 
-// y[i*L] = x[i]; other outputs zero.  One thread per OUTPUT element so the writes (the
-// L-times larger side) are perfectly coalesced; reads hit the same x element L times in a row
-// (served by L1/L2).
+// y[i*L] = x[i]; other outputs zero.  Threads own 16-byte OUTPUT vectors (the L-times larger
+// side) so stores are full-width and perfectly coalesced; one integer division per vector, the
+// element index then advances incrementally.  Reads touch each x element once per vector that
+// overlaps its row (L1/L2 hits).
+template <typename E, typename IDX>
+__global__ void __launch_bounds__(256) upsample_vec_kernel(const E *__restrict__ x, E *__restrict__ y,
+                                                          int64_t n_out, int32_t L)
+{
+    constexpr int VEC = 16 / (int)sizeof(E);
+    struct __align__(16) Pack { E v[VEC]; };
+    const int64_t n_vec = n_out / VEC;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t vi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; vi < n_vec; vi += stride) {
+        const IDX o = (IDX)(vi * VEC);
+        IDX q = o / (IDX)L;
+        int r = (int)(o - q * (IDX)L);
+        Pack pk;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            pk.v[e] = (r == 0) ? x[q] : zero_of(E());
+            if (++r == L) { r = 0; ++q; }
+        }
+        reinterpret_cast<Pack *>(y)[vi] = pk;
+    }
+    // tail (n_out not a multiple of VEC)
+    const int64_t t = n_vec * VEC + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_out) {
+        int64_t q = t / L;
+        y[t] = (q * L == t) ? x[q] : zero_of(E());
+    }
+}
+
 template <typename E>
 __global__ void __launch_bounds__(256) upsample_kernel(const E *__restrict__ x, E *__restrict__ y,
                                                       int64_t n_out, int32_t L)
@@ -56,7 +85,16 @@ template <typename E>
 static int up_launch(const void *x, void *y, int64_t n, int32_t L, cudaStream_t st)
 {
     int64_t n_out = n * L;
-    upsample_kernel<E><<<grid_for(n_out, sm_count_cached()), 256, 0, st>>>((const E *)x, (E *)y, n_out, L);
+    constexpr int VEC = 16 / (int)sizeof(E);
+    if ((reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+        unsigned g = grid_for((n_out + VEC - 1) / VEC, sm_count_cached());
+        if (n_out < (int64_t)1 << 31)
+            upsample_vec_kernel<E, uint32_t><<<g, 256, 0, st>>>((const E *)x, (E *)y, n_out, L);
+        else
+            upsample_vec_kernel<E, int64_t><<<g, 256, 0, st>>>((const E *)x, (E *)y, n_out, L);
+    } else {
+        upsample_kernel<E><<<grid_for(n_out, sm_count_cached()), 256, 0, st>>>((const E *)x, (E *)y, n_out, L);
+    }
     B200_CHECK_LAUNCH("upsample_kernel");
     return B200DSP_OK;
 }

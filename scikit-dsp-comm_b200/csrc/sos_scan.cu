@@ -5,11 +5,11 @@
 // direct-form-II-transposed loop; here the same recurrence is evaluated in
 // three launches per group of <= 8 sections:
 //
-//   K1 sos_pass1   one block per tile of T = 512*LC samples.  The tile is staged in shared
+//   K1 sos_pass1   one block per tile of T = SOS_NT*LC samples.  The tile is staged in shared
 //                  memory TRANSPOSED (sample n of chunk t at [n][t]) so that thread t can walk
 //                  its own LC-sample chunk with conflict-free accesses.  Each thread runs the
 //                  cascade over its chunk from ZERO state and keeps the 2*nsec final state
-//                  values ("chunk carry").  A Kogge-Stone scan over the 512 carries with the
+//                  values ("chunk carry").  A Kogge-Stone scan over the SOS_NT carries with the
 //                  constant matrices A^(LC*2^j) (the cascade is LTI, so only state VECTORS are
 //                  scanned, never matrices) yields the tile carry.  Chunk carries and the
 //                  tile carry go to the workspace.
@@ -27,8 +27,9 @@
 
 namespace b200dsp {
 
-constexpr int SOS_NT = 512;          // threads per block in K1/K3
-constexpr int SOS_LEVELS = 9;        // log2(SOS_NT)
+constexpr int SOS_NT = 256;          // threads per block in K1/K3 (256 -> 2-3 resident blocks/SM so
+                                     // one block's tile load overlaps another block's recurrence)
+constexpr int SOS_LEVELS = 8;        // log2(SOS_NT)
 constexpr int SOS_MAXSEC = 8;        // sections per launch group
 constexpr int SOS_K2_NT = 256;       // threads in the tile-scan block
 constexpr int SOS_K2_LEVELS = 8;
@@ -353,7 +354,7 @@ struct SosGroup {
     int nsec_real;                     // sections that came from the user's sos
     double coef[SOS_MAXSEC][5];        // b0 b1 b2 -a1 -a2
     std::vector<double> A;             // D x D one-sample state transition
-    std::vector<double> tileA[3];      // A^(512*LC) for LC = 16,32,64
+    std::vector<double> tileA[3];      // A^(SOS_NT*LC) for LC = 16,32,64
     float *mats_f32[3];                // device [SOS_LEVELS][D*D], per LC
     double *mats_f64[3];
 };
@@ -597,7 +598,7 @@ int b200dsp_sos_plan_create(const double *sos_host, int32_t nsec, b200dsp_sos_pl
                 memcpy(all.data() + (size_t)j * D * D, pw.data(), sizeof(double) * D * D);
                 matmul(pw, pw, pw, D);
             }
-            g.tileA[li] = pw;       // A^(lc * 512)
+            g.tileA[li] = pw;       // A^(lc * SOS_NT)
             std::vector<float> allf(all.begin(), all.end());
             e = cudaMalloc(&g.mats_f32[li], allf.size() * sizeof(float));
             if (e == cudaSuccess) e = cudaMalloc(&g.mats_f64[li], all.size() * sizeof(double));

@@ -232,7 +232,7 @@ def test_fir_halo_equals_monolithic(mods, filters):
         assert torch.equal(yd[cut // 4:], yd2)
 
 
-@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 32767, 32768, 32769, 100003])
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 4095, 4096, 4097, 16383, 16384, 16385, 32769, 100003])
 @pytest.mark.parametrize("dt", ["float32", "complex64", "float64", "complex128"])
 def test_sos_sizes_across_tile_boundaries(mods, filters, n, dt):
     rng = np.random.default_rng(n + 3)
