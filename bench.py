@@ -233,7 +233,7 @@ def run_gpu(args):
     achieved = ALGO_BYTES_PER_SAMPLE * n / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": dram_traffic_per_launch(),
-                "peak_source": peak_src, "kernel": "fir_poly_kernel<float2,float,32,128,packed FFMA2>",
+                "peak_source": peak_src, "kernel": "fir_tc_kernel (tcgen05 block-Toeplitz, fp16 hi/lo split)" if args.variant in (0, 10) else "fir_poly_kernel<float2,float,R,NT>",
                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SAMPLE * n,
                 "kernel_ms": k_ms, "kernel_ms_min": min(per_step)}
 
@@ -266,7 +266,9 @@ def run_gpu(args):
                "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3,
                "api": "multirate_FIR(b).filter(pinned host tensor) -> host tensor"}
         # sanity: host path result == device path result on a window
-        assert torch.equal(yh[:4096], step()[:4096].cpu()) if world == 1 else True
+        if world == 1:
+            yd = step()[:4096].cpu()
+            assert (yh[:4096] - yd).abs().max().item() <= 1e-6 * yd.abs().max().item()
 
     if rank == 0:
         line = {

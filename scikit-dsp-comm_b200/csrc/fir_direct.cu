@@ -161,7 +161,17 @@ struct b200dsp_fir_plan_impl {
     int32_t ntaps;
     float *taps_f32;
     double *taps_f64;
+    void *tc_bmat;       // tensor-core path: swizzled fp16 hi/lo Toeplitz tap matrices (or NULL)
+    int32_t tc_sb_exp;
+    int32_t sm_count;
 };
+
+// fir_tc.cu
+int tc_build_tap_matrices(const double *taps, int ntaps, unsigned char *out, int *sb_exp);
+int tc_matrix_bytes();
+int tc_max_taps();
+int launch_fir_tc(const void *x, const void *hist, void *y, int64_t n, int32_t hist_len,
+                  const void *bmat_dev, int sb_exp, int bo_mode, int sm_count, cudaStream_t stream);
 
 static thread_local int g_fir_variant = 0;
 
@@ -255,6 +265,10 @@ static int fir_dispatch(const b200dsp_fir_plan_impl *p, int dtype, const void *x
         if (v == 1) return launch_fir_fit<float, 16>(p, x, hist, y, n, n_m, L, M, hist_len, s, 256);
         return launch_fir_fit<float, 32>(p, x, hist, y, n, n_m, L, M, hist_len, s, 128);
     case B200DSP_C64:
+        // default for long complex64 streams: block-Toeplitz GEMM on the tensor cores (fir_tc.cu).
+        // v == 10 forces it for any length, v == 9 forces the CUDA-core kernel.
+        if (((v == 0 && n >= 32768) || v == 10) && L == 1 && M == 1 && p->tc_bmat != nullptr)
+            return launch_fir_tc(x, hist, y, n, hist_len, p->tc_bmat, p->tc_sb_exp, 0, p->sm_count, s);
         if (v == 1) return launch_fir_fit<float2, 16>(p, x, hist, y, n, n_m, L, M, hist_len, s, 256);
         if (v == 2) return launch_fir_fit<float2, 16>(p, x, hist, y, n, n_m, L, M, hist_len, s, 128);
         if (v == 3) return launch_fir_fit<float2, 32>(p, x, hist, y, n, n_m, L, M, hist_len, s, 128);
@@ -290,6 +304,14 @@ int b200dsp_fir_plan_create(const double *taps_host, int32_t ntaps, b200dsp_fir_
     p->ntaps = ntaps;
     p->taps_f32 = nullptr;
     p->taps_f64 = nullptr;
+    p->tc_bmat = nullptr;
+    p->tc_sb_exp = 0;
+    p->sm_count = 148;
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess)
+            cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, dev);
+    }
     float *tmp = new float[ntaps];
     for (int i = 0; i < ntaps; ++i) tmp[i] = (float)taps_host[i];
     cudaError_t e = cudaMalloc(&p->taps_f32, sizeof(float) * ntaps);
@@ -297,10 +319,20 @@ int b200dsp_fir_plan_create(const double *taps_host, int32_t ntaps, b200dsp_fir_
     if (e == cudaSuccess) e = cudaMemcpy(p->taps_f32, tmp, sizeof(float) * ntaps, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(p->taps_f64, taps_host, sizeof(double) * ntaps, cudaMemcpyHostToDevice);
     delete[] tmp;
+    if (e == cudaSuccess && ntaps <= tc_max_taps()) {
+        const int nb = tc_matrix_bytes();
+        unsigned char *hb = new unsigned char[nb];
+        if (tc_build_tap_matrices(taps_host, ntaps, hb, &p->tc_sb_exp) == 0) {
+            e = cudaMalloc(&p->tc_bmat, nb);
+            if (e == cudaSuccess) e = cudaMemcpy(p->tc_bmat, hb, nb, cudaMemcpyHostToDevice);
+        }
+        delete[] hb;
+    }
     if (e != cudaSuccess) {
         set_error("fir_plan_create: %s", cudaGetErrorString(e));
         cudaFree(p->taps_f32);
         cudaFree(p->taps_f64);
+        cudaFree(p->tc_bmat);
         delete p;
         return B200DSP_E_CUDA;
     }
@@ -313,6 +345,7 @@ void b200dsp_fir_plan_destroy(b200dsp_fir_plan *plan)
     if (!plan) return;
     cudaFree(plan->taps_f32);
     cudaFree(plan->taps_f64);
+    cudaFree(plan->tc_bmat);
     delete plan;
 }
 
