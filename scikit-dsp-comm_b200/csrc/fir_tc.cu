@@ -79,6 +79,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int who
     printf("b200dsp fir_tc: mbarrier timeout (role %d, block %d)\n", who, (int)blockIdx.x);
     __trap();
 }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -278,34 +283,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(const Args a)
         }
     } else if (warp == MMA_WARP) {
         // =============================== MMA issuer ===============================
-        if (lane == 0) {
-            int it = 0;
-            for (int64_t tile = first; tile < a.n_tiles; tile += step, ++it) {
-                const int s = it & 1;
-                mbar_wait(BAR(0 + s), (it >> 1) & 1, 2);              // operands staged
-                mbar_wait(BAR(6 + s), ((it >> 1) & 1) ^ 1, 3);        // accumulators drained
-                tc_fence_after();
+        // Uniform control flow for the whole warp; one elected lane issues (no per-lane UTCHMMA loop).
+        int it = 0;
+        for (int64_t tile = first; tile < a.n_tiles; tile += step, ++it) {
+            const int s = it & 1;
+            mbar_wait(BAR(0 + s), (it >> 1) & 1, 2);              // operands staged
+            mbar_wait(BAR(6 + s), ((it >> 1) & 1) ^ 1, 3);        // accumulators drained
+            tc_fence_after();
+            if (elect_one()) {
                 const uint32_t a_base = base + SMEM_A_OFF + s * STAGE_BYTES;
                 const uint32_t b_hi = base + SMEM_B_OFF, b_lo = b_hi + B_BYTES;
                 const uint32_t d_stage = tmem_base + (uint32_t)s * 256u;
-#pragma unroll 1
+#pragma unroll
                 for (int ch = 0; ch < 2; ++ch) {
                     const uint32_t a_hi = a_base + (2 * ch) * STREAM_BYTES, a_lo = a_hi + STREAM_BYTES;
                     const uint32_t d1 = d_stage + ch * 128, d2 = d1 + 64;
-#pragma unroll 1
+#pragma unroll
                     for (int pass = 0; pass < 3; ++pass) {
-                        const uint32_t as = (pass == 2) ? a_lo : a_hi;
-                        const uint32_t bs = (pass == 1) ? b_lo : b_hi;
+                        const uint64_t ad0 = make_desc((pass == 2) ? a_lo : a_hi, 0);
+                        const uint64_t bd0 = make_desc((pass == 1) ? b_lo : b_hi, 0);
                         const uint32_t dd = (pass == 0) ? d1 : d2;
 #pragma unroll
                         for (int jj = 0; jj < NKB; ++jj) {
-                            const uint32_t j = (a.kb_order >> (4 * jj)) & 15u;
+                            constexpr int kOrder[NKB] = {0, 1, 4, 3, 2};
+                            const int j = kOrder[jj];
 #pragma unroll
                             for (int sl = 0; sl < 4; ++sl) {
-                                const uint32_t aaddr = as + 128u * j + 32u * sl;
-                                const uint32_t baddr = bs + (uint32_t)B_KB_BYTES * j + 32u * sl;
-                                const uint64_t ad = make_desc(aaddr, a.bo_mode ? (aaddr >> 7) : 0);
-                                const uint64_t bd = make_desc(baddr, 0);
+                                const uint64_t ad = ad0 + (uint64_t)(8 * j + 2 * sl);
+                                const uint64_t bd = bd0 + (uint64_t)((B_KB_BYTES >> 4) * j + 2 * sl);
                                 const uint32_t acc = (pass == 2) ? 1u : ((jj | sl) ? 1u : 0u);
                                 if (!(a.dbg & 1)) umma_f16(dd, ad, bd, kIdesc, acc);
                             }
@@ -315,8 +320,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_kernel(const Args a)
                 umma_commit(BAR(2 + s));        // stage s may be overwritten
                 umma_commit(BAR(4 + s));        // accumulators of this tile are complete
             }
+            __syncwarp();
         }
-        __syncwarp();
     } else {
         // =============================== epilogue ===============================
         int it = 0;

@@ -1,0 +1,536 @@
+// fir_tc2.cu -- complex64 FIR on tcgen05, "taps-stationary" formulation (second generation).
+//
+// fir_tc.cu showed that the block-Toeplitz GEMM is limited by the tensor core's SHARED-MEMORY operand
+// fetch (~64 B/clk/SM: 96 cycles per 128x64x16 MMA instead of 32; ncu: tensor pipe 33 % active).
+// Here the tap matrix -- the operand that never changes -- lives in TENSOR MEMORY for the whole
+// kernel, so only the sample stream is fetched from shared memory:
+//
+//     D[rho, r] = sum_{kk<320} A[rho, kk] * B[r, kk]
+//       A (TMEM, 128 lanes x 160 columns, written once per CTA with tcgen05.st):
+//           row rho = (c, part): Toeplitz row T[c][kk] = b[c + 256 - kk] * 2^sb, part in {fp16 hi, fp16 lo};
+//           rows are interleaved so that lanes l and l+16 of one warp hold hi and lo of the same c
+//       B (shared memory, K-major SWIZZLE_128B, never materialised as a Hankel matrix):
+//           row r = the fp16 sample stream starting at sample t0 - 256 + 64 r: k-block j of the UMMA
+//           descriptor simply starts 128*j bytes later in the SAME stream (one swizzle row = 64 fp16)
+//       D (TMEM accumulators, fp32): lanes = (c, part), columns = r  ->  y[t0 + 64 r + c]
+//
+// One MMA (M=128,N=64,K=16) now reads 2 KB from shared memory instead of 6 KB and produces both the
+// b_hi*x and b_lo*x products.  Per complex sample: 2 channels x 2 sample parts (x_hi, x_lo) x 20 k-slices.
+//   y = (hh + 2^-11 (lh + hl)) / (s_x s_b),  hh = b_hi*x_hi, lh = b_lo*x_hi, hl = b_hi*x_lo (ll dropped).
+//
+// Data movement: a producer thread streams raw complex64 tiles (34 KB) into a 6-deep shared-memory
+// ring with 1-D bulk TMA (cp.async.bulk + mbarrier complete_tx); converter warps turn a stage IN PLACE
+// into four swizzled fp16 streams (re/im x hi/lo) around a per-tile power-of-two scale; the MMA thread
+// consumes it; tcgen05.commit recycles the stage.  Accumulators are double buffered per channel so the
+// epilogue (TMEM -> registers -> shuffle-combine hi/lo lanes -> coalesced complex64 stores) overlaps
+// the next channel's MMAs.
+#include "common.cuh"
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+namespace b200dsp {
+namespace tc2 {
+
+constexpr int BK = 64;                       // fp16 per 128-byte swizzle row = outputs per GEMM column block
+constexpr int NKB = 5;                       // k-blocks (256 taps + 64) / 64
+constexpr int KTOT = NKB * BK;               // 320
+template <int TN> struct Cfg {
+    static constexpr int TILE_N = TN;                    // stream rows (GEMM N) per tile: 64 or 128
+    static constexpr int TILE = TILE_N * BK;             // complex outputs per tile
+    static constexpr int ROWS = TILE_N + NKB - 1;        // stream rows staged per tile
+    static constexpr int TILE_IN = ROWS * BK;            // complex samples staged per tile
+    static constexpr int RAW_BYTES = TILE_IN * 8;
+    static constexpr int STREAM_BYTES = ((ROWS * 128 + 1023) / 1024) * 1024;
+    static constexpr int STAGE_BYTES = 4 * STREAM_BYTES; // >= RAW_BYTES: converted in place
+    static constexpr int NSTAGE = (TN == 64) ? 6 : 3;
+    static constexpr int SMEM_BAR_OFF = NSTAGE * STAGE_BYTES;
+    static constexpr int SMEM_TOTAL = SMEM_BAR_OFF + 512 + 1024;
+    static constexpr int ACC_BUF_COLS = TILE_N;          // one fp32 accumulator (128 lanes x TILE_N stream rows) per (tile, channel)
+    static constexpr int NACC = (TN == 64) ? 4 : 2;      // accumulator ring depth
+    static constexpr int F4_PER_TILE = TILE_IN / 2;
+    static constexpr int F4_PER_THREAD = (F4_PER_TILE + 255) / 256;
+    static constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    static_assert((4 * STREAM_BYTES) >= (TILE_IN * 8), "in-place conversion: stage must hold the raw tile");
+};
+constexpr int HALO = (NKB - 1) * BK;         // 256
+
+constexpr int A_COLS = KTOT / 2;             // 160 TMEM columns of packed fp16 pairs
+constexpr int ACC_COL0 = A_COLS;             // accumulators start here
+
+constexpr int N_EPI_WARPS = 4;               // warps 0-3 (TMEM lanes 32w..32w+31)
+constexpr int MMA_WARP = 4;
+constexpr int PROD_WARP = 5;
+constexpr int CVT_WARP0 = 6;
+constexpr int N_CVT_WARPS = 8;
+constexpr int N_CVT = N_CVT_WARPS * 32;      // 256
+constexpr int NTHREADS = (CVT_WARP0 + N_CVT_WARPS) * 32;    // 448
+constexpr int INV_RING = 16;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int who) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; spin < (1u << 27); ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+    }
+    printf("b200dsp fir_tc2: mbarrier timeout (role %d, block %d)\n", who, (int)blockIdx.x);
+    __trap();
+}
+// bring-up instrumentation: cycles spent inside a wait, accumulated per call site
+template <bool DBG>
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, int who, long long &acc) {
+    if constexpr (DBG) {
+        long long t0 = clock64();
+        mbar_wait(bar, parity, who);
+        acc += clock64() - t0;
+    } else {
+        mbar_wait(bar, parity, who);
+    }
+}
+// one elected lane of a converged warp (lets ptxas emit UTCHMMA / UBLKCP without a lane loop)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B descriptor (see fir_tc.cu; the swizzle is a function of the absolute shared
+// address, so a start address that is not 1024-aligned needs base_offset = 0 -- measured on B200)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+struct Args {
+    const float2 *x;
+    const float2 *hist;
+    float2 *y;
+    const uint4 *amat;        // device: 128 rows x 320 fp16 (row = TMEM lane), row-major
+    int64_t n;
+    int64_t n_tiles;
+    int32_t hist_len;
+    int32_t sb_exp;
+    int32_t jmin;             // first k-block that holds a non-zero tap (short filters skip the rest)
+    int32_t dbg;              // bring-up: bit0 skip MMAs, bit1 skip conversion, bit2 skip stores
+};
+
+__device__ __forceinline__ float2 load_sample(const Args &a, int64_t g) {
+    if (g >= 0) return (g < a.n) ? a.x[g] : make_float2(0.f, 0.f);
+    if (a.hist != nullptr) {
+        int64_t h = (int64_t)a.hist_len + g;
+        if (h >= 0) return a.hist[h];
+    }
+    return make_float2(0.f, 0.f);
+}
+template <int TN>
+__device__ __forceinline__ bool tile_is_bulk(const Args &a, int64_t tile) {
+    const int64_t g0 = tile * Cfg<TN>::TILE - HALO;
+    return g0 >= 0 && g0 + Cfg<TN>::TILE_IN <= a.n && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0);
+}
+__device__ __forceinline__ uint32_t stream_off(int e) {
+    const int row = e >> 6, col = e & 63;
+    return (uint32_t)(row * 128 + ((((col >> 3) ^ (row & 7))) << 4) + ((col & 7) << 1));
+}
+
+template <int TN, bool DBG>
+__global__ void __launch_bounds__(NTHREADS, 1) fir_tc2_kernel(const Args a)
+{
+    using C = Cfg<TN>;
+    constexpr int TILE_N = C::TILE_N, TILE = C::TILE, TILE_IN = C::TILE_IN, RAW_BYTES = C::RAW_BYTES;
+    constexpr int STREAM_BYTES = C::STREAM_BYTES, STAGE_BYTES = C::STAGE_BYTES, NSTAGE = C::NSTAGE;
+    constexpr int SMEM_BAR_OFF = C::SMEM_BAR_OFF, ACC_BUF_COLS = C::ACC_BUF_COLS, NACC = C::NACC;
+    constexpr int F4_PER_TILE = C::F4_PER_TILE, F4_PER_THREAD = C::F4_PER_THREAD;
+    constexpr uint32_t kIdesc = C::kIdesc;
+    (void)TILE_IN;
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t raw_base = smem_u32(smem_dyn);
+    const uint32_t base = (raw_base + 1023u) & ~1023u;
+    unsigned char *sm = smem_dyn + (base - raw_base);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + SMEM_BAR_OFF);
+    const uint32_t bar0 = base + SMEM_BAR_OFF;
+    // raw_full[s]=s, a_full[s]=6+s, a_empty[s]=12+s, d_full[b]=18+b, d_empty[b]=20+b
+    auto RAW_FULL = [&](int s) { return bar0 + 8u * s; };
+    auto A_FULL = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
+    auto A_EMPTY = [&](int s) { return bar0 + 8u * (2 * NSTAGE + s); };
+    auto D_FULL = [&](int b) { return bar0 + 8u * (3 * NSTAGE + b); };
+    auto D_EMPTY = [&](int b) { return bar0 + 8u * (3 * NSTAGE + NACC + b); };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * NSTAGE + 2 * NACC);
+    float *wmax = reinterpret_cast<float *>(bars + 3 * NSTAGE + 2 * NACC + 1);          // 8 floats
+    float *tile_inv = reinterpret_cast<float *>(bars + 3 * NSTAGE + 2 * NACC + 5);      // INV_RING floats
+
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(RAW_FULL(s), 1);
+            mbar_init(A_FULL(s), N_CVT_WARPS);
+            mbar_init(A_EMPTY(s), 1);
+        }
+        for (int b = 0; b < NACC; ++b) {
+            mbar_init(D_FULL(b), 1);
+            mbar_init(D_EMPTY(b), N_EPI_WARPS);
+        }
+        fence_barrier_init();
+    }
+    if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // ---- tap matrix -> TMEM (A operand, stays for the whole kernel) ----
+    if (warp < N_EPI_WARPS) {
+        const int row = warp * 32 + lane;                                  // TMEM lane == matrix row
+        const uint4 *src = a.amat + (size_t)row * (KTOT * 2 / 16);         // 40 uint4 per row
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < A_COLS; c0 += 16) {
+            uint32_t v[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint4 u = src[c0 / 4 + q];
+                v[4 * q + 0] = u.x; v[4 * q + 1] = u.y; v[4 * q + 2] = u.z; v[4 * q + 3] = u.w;
+            }
+            tmem_st16(taddr + c0, v);
+        }
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    const int64_t first = blockIdx.x, step = gridDim.x;
+
+    if (warp == PROD_WARP) {
+        // =============================== producer (bulk TMA) ===============================
+        int it = 0;
+        long long w0 = 0, t_start = DBG ? clock64() : 0;
+        for (int64_t tile = first; tile < a.n_tiles; tile += step, ++it) {
+            const int s = it % NSTAGE;
+            const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
+            mbar_wait_t<DBG>(A_EMPTY(s), ph ^ 1u, 0, w0);
+            if (elect_one()) {
+                if (tile_is_bulk<TN>(a, tile)) {
+                    mbar_arrive_expect_tx(RAW_FULL(s), RAW_BYTES);
+                    bulk_g2s(base + s * STAGE_BYTES, a.x + (tile * TILE - HALO), RAW_BYTES, RAW_FULL(s));
+                } else {
+                    mbar_arrive(RAW_FULL(s));       // edge tile: converters fetch it with guarded loads
+                }
+            }
+            __syncwarp();
+        }
+        if (DBG && (a.dbg & 8) && blockIdx.x == 1 && lane == 0)
+            printf("tc2 producer: tiles %d total %lld wait_a_empty %lld\n", it, clock64() - t_start, w0);
+    } else if (warp >= CVT_WARP0) {
+        // =============================== converters ===============================
+        const int ct = tid - CVT_WARP0 * 32;
+        int it = 0;
+        long long w0 = 0, t_start = DBG ? clock64() : 0;
+        for (int64_t tile = first; tile < a.n_tiles; tile += step, ++it) {
+            const int s = it % NSTAGE;
+            const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
+            unsigned char *st = sm + s * STAGE_BYTES;
+            mbar_wait_t<DBG>(RAW_FULL(s), ph, 1, w0);
+            float4 raw4[F4_PER_THREAD];
+            const bool bulk = tile_is_bulk<TN>(a, tile);
+            const int64_t g0 = tile * TILE - HALO;
+#pragma unroll
+            for (int i = 0; i < F4_PER_THREAD; ++i) {
+                const int f = ct + i * N_CVT;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (f < F4_PER_TILE) {
+                    if (bulk) {
+                        v = reinterpret_cast<const float4 *>(st)[f];
+                    } else {
+                        float2 s0 = load_sample(a, g0 + 2 * f), s1 = load_sample(a, g0 + 2 * f + 1);
+                        v = make_float4(s0.x, s0.y, s1.x, s1.y);
+                    }
+                }
+                raw4[i] = v;
+            }
+            float m = 0.f;
+#pragma unroll
+            for (int i = 0; i < F4_PER_THREAD; ++i)
+                m = fmaxf(fmaxf(m, fmaxf(fabsf(raw4[i].x), fabsf(raw4[i].y))), fmaxf(fabsf(raw4[i].z), fabsf(raw4[i].w)));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            asm volatile("bar.sync 1, %0;" ::"n"(N_CVT));        // wmax free; (in place) nobody writes yet
+            if (lane == 0) wmax[warp - CVT_WARP0] = m;
+            asm volatile("bar.sync 1, %0;" ::"n"(N_CVT));        // every thread holds its raw samples in registers
+            float bm = 0.f;
+#pragma unroll
+            for (int w = 0; w < N_CVT_WARPS; ++w) bm = fmaxf(bm, wmax[w]);
+            int ex = 14;
+            if (bm > 0.f && bm < 3.0e38f) (void)frexpf(bm, &ex);
+            int e = max(-110, min(110, 14 - ex));
+            const float sx = ldexpf(1.0f, e);
+            if (!DBG || !(a.dbg & 2)) {
+                // element e = 2f lives at row f>>5, 16-byte chunk (f&31)>>2: the swizzled offset of this
+                // thread's pair advances by exactly 8 rows (1024 B) per iteration
+                const uint32_t off0 = stream_off(2 * ct);
+#pragma unroll
+                for (int i = 0; i < F4_PER_THREAD; ++i) {
+                    const int f = ct + i * N_CVT;
+                    if (f < F4_PER_TILE) {
+                        const float4 v = raw4[i];
+                        const float re0 = v.x * sx, im0 = v.y * sx, re1 = v.z * sx, im1 = v.w * sx;
+                        const __half2 rh = __floats2half2_rn(re0, re1);
+                        const __half2 ih = __floats2half2_rn(im0, im1);
+                        const float2 rhf = __half22float2(rh), ihf = __half22float2(ih);
+                        // lo = true residual (not rescaled): products land in the same accumulator as hi*hi
+                        const __half2 rl = __floats2half2_rn(re0 - rhf.x, re1 - rhf.y);
+                        const __half2 il = __floats2half2_rn(im0 - ihf.x, im1 - ihf.y);
+                        const uint32_t off = off0 + (uint32_t)i * 1024u;
+                        *reinterpret_cast<__half2 *>(st + 0 * STREAM_BYTES + off) = rh;
+                        *reinterpret_cast<__half2 *>(st + 1 * STREAM_BYTES + off) = rl;
+                        *reinterpret_cast<__half2 *>(st + 2 * STREAM_BYTES + off) = ih;
+                        *reinterpret_cast<__half2 *>(st + 3 * STREAM_BYTES + off) = il;
+                    }
+                }
+            }
+            if (ct == 0) tile_inv[it % INV_RING] = ldexpf(1.0f, -e - a.sb_exp);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(A_FULL(s));
+        }
+        if (DBG && (a.dbg & 8) && blockIdx.x == 1 && ct == 0)
+            printf("tc2 converter: tiles %d total %lld wait_raw_full %lld\n", it, clock64() - t_start, w0);
+    } else if (warp == MMA_WARP) {
+        // =============================== MMA issuer ===============================
+        // The whole warp runs the loop (uniform control flow); one elected lane issues, so ptxas emits the
+        // UTCHMMA sequence without a per-lane serialisation loop (measured: ~76 -> ~16 cycles per issue).
+        int it = 0;
+        uint32_t unit = 0;                             // (tile, channel) counter -> accumulator buffer
+        long long w0 = 0, w1 = 0, t_start = DBG ? clock64() : 0;
+        for (int64_t tile = first; tile < a.n_tiles; tile += step, ++it) {
+            const int s = it % NSTAGE;
+            const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
+            mbar_wait_t<DBG>(A_FULL(s), ph, 2, w0);
+            tc_fence_after();
+            const uint32_t st = base + s * STAGE_BYTES;
+#pragma unroll 1
+            for (int ch = 0; ch < 2; ++ch, ++unit) {
+                const uint32_t b = unit % NACC;
+                mbar_wait_t<DBG>(D_EMPTY(b), ((unit / NACC) & 1u) ^ 1u, 3, w1);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t dd = tmem_base + ACC_COL0 + b * ACC_BUF_COLS;
+                    // The x_lo stream goes FIRST: its products are ~2^-11 of the result, so the accumulator is
+                    // still tiny while they are added and the tensor core's truncating fp32 adds cost nothing;
+                    // then x_hi with the small (outer) tap blocks before the large centre ones.
+                    uint32_t started = 0;
+#pragma unroll
+                    for (int pp = 0; pp < 2; ++pp) {
+                        const int part = 1 - pp;
+                        // descriptor of (stream, k-block 0, slice 0); only the 14-bit start field changes
+                        const uint64_t bd0 = make_desc(st + (2 * ch + part) * STREAM_BYTES);
+#pragma unroll
+                        for (int jj = 0; jj < NKB; ++jj) {
+                            constexpr int kOrder[NKB] = {0, 1, 4, 3, 2};
+                            const int j = kOrder[jj];
+                            if (j < a.jmin) continue;                  // all-zero tap block (filter shorter than 256)
+#pragma unroll
+                            for (int sl = 0; sl < 4; ++sl) {
+                                const uint64_t bd = bd0 + (uint64_t)(8 * j + 2 * sl);     // +128 j + 32 sl bytes (>>4)
+                                const uint32_t at = tmem_base + (j * 4 + sl) * 8;
+                                if (!DBG || !(a.dbg & 1)) umma_f16_ts(dd, at, bd, kIdesc, started);
+                                started = 1;
+                            }
+                        }
+                    }
+                    umma_commit(D_FULL(b));
+                    if (ch == 1) umma_commit(A_EMPTY(s));
+                }
+                __syncwarp();
+            }
+        }
+        if (DBG && (a.dbg & 8) && blockIdx.x == 1 && lane == 0)
+            printf("tc2 mma: tiles %d total %lld wait_a_full %lld wait_d_empty %lld\n", it, clock64() - t_start, w0, w1);
+    } else {
+        // =============================== epilogue (warps 0-3) ===============================
+        // Lane l < 16 holds row b_hi[c], lane l+16 row b_lo[c] (c = 16*warp + l): y = (D[l] + D[l+16]) * inv.
+        // Hi-row lanes finish even stream rows, lo-row lanes the odd ones, so all 32 lanes store.
+        int it = 0;
+        uint32_t unit = 0;
+        const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+        const bool lo_row = lane >= 16;
+        const int c = warp * 16 + (lane & 15);
+        long long w0 = 0, t_start = DBG ? clock64() : 0;
+        for (int64_t tile = first; tile < a.n_tiles; tile += step, ++it, unit += 2) {
+            const uint32_t b_re = unit % NACC, b_im = (unit + 1) % NACC;
+            mbar_wait_t<DBG>(D_FULL(b_re), (unit / NACC) & 1u, 4, w0);
+            mbar_wait_t<DBG>(D_FULL(b_im), ((unit + 1) / NACC) & 1u, 4, w0);
+            tc_fence_after();
+            const float inv = tile_inv[it % INV_RING];
+            const uint32_t d_re = tmem_base + lane_sel + ACC_COL0 + b_re * ACC_BUF_COLS;
+            const uint32_t d_im = tmem_base + lane_sel + ACC_COL0 + b_im * ACC_BUF_COLS;
+            const int64_t g_c = tile * TILE + c + (lo_row ? BK : 0);
+#pragma unroll 1
+            for (int c0 = 0; c0 < TILE_N; c0 += 16) {
+                uint32_t dr[16], di[16];
+                tmem_ld16(d_re + c0, dr);
+                tmem_ld16(d_im + c0, di);
+                tmem_ld_wait();
+                if (c0 + 16 == TILE_N) {                     // both accumulators are in registers: release them
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) { mbar_arrive(D_EMPTY(b_re)); mbar_arrive(D_EMPTY(b_im)); }
+                }
+#pragma unroll
+                for (int q = 0; q < 16; q += 2) {
+                    const float sr = __uint_as_float(lo_row ? dr[q] : dr[q + 1]);
+                    const float si = __uint_as_float(lo_row ? di[q] : di[q + 1]);
+                    const float rr = __shfl_xor_sync(0xffffffffu, sr, 16);
+                    const float ri = __shfl_xor_sync(0xffffffffu, si, 16);
+                    const float vr = (rr + __uint_as_float(lo_row ? dr[q + 1] : dr[q])) * inv;
+                    const float vi = (ri + __uint_as_float(lo_row ? di[q + 1] : di[q])) * inv;
+                    const int64_t g = g_c + (int64_t)(c0 + q) * BK;
+                    if ((!DBG || !(a.dbg & 4)) && g < a.n) a.y[g] = make_float2(vr, vi);
+                }
+            }
+        }
+        if (DBG && (a.dbg & 8) && blockIdx.x == 1 && tid == 0)
+            printf("tc2 epilogue: tiles %d total %lld wait_d_full %lld\n", it, clock64() - t_start, w0);
+    }
+    // ---- teardown ----
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace tc2
+
+// ------------------------------------------------------------------------------------------ host
+// 128 x 320 fp16 row-major tap matrix for the TMEM A operand.  Row rho = 32 w + l:
+//   l < 16 : hi part of Toeplitz row c = 16 w + l;   l >= 16 : lo part of row c = 16 w + l - 16
+int tc2_build_tap_matrix(const double *taps, int ntaps, unsigned char *out, int *sb_exp)
+{
+    using namespace tc2;
+    if (ntaps > HALO) return -1;
+    double mx = 0.0;
+    for (int i = 0; i < ntaps; ++i) mx = fmax(mx, fabs(taps[i]));
+    int ex = 0;
+    if (mx > 0.0) (void)frexp(mx, &ex);
+    int e = 12 - ex;
+    if (e > 60) e = 60;
+    if (e < -60) e = -60;
+    *sb_exp = e;
+    __half *m = reinterpret_cast<__half *>(out);
+    for (int rho = 0; rho < 128; ++rho) {
+        const int w = rho / 32, l = rho % 32;
+        const int c = 16 * w + (l & 15);
+        const bool lo = l >= 16;
+        for (int kk = 0; kk < KTOT; ++kk) {
+            int t = c + HALO - kk;
+            double v = (t >= 0 && t < ntaps) ? ldexp(taps[t], e) : 0.0;
+            __half hi = __float2half_rn((float)v);
+            __half lw = __float2half_rn((float)(v - (double)__half2float(hi)));   // true residual
+            m[(size_t)rho * KTOT + kk] = lo ? lw : hi;
+        }
+    }
+    return 0;
+}
+int tc2_matrix_bytes() { return 128 * tc2::KTOT * 2; }
+
+template <int TN, bool DBG>
+static int launch_tc2_cfg(tc2::Args a, int64_t n, int sm_count, cudaStream_t stream)
+{
+    using namespace tc2;
+    a.n_tiles = (n + Cfg<TN>::TILE - 1) / Cfg<TN>::TILE;
+    auto kern = fir_tc2_kernel<TN, DBG>;
+    B200_CHECK_CUDA(allow_smem(kern, Cfg<TN>::SMEM_TOTAL));
+    int64_t grid = a.n_tiles < sm_count ? a.n_tiles : sm_count;
+    kern<<<(unsigned)grid, NTHREADS, Cfg<TN>::SMEM_TOTAL, stream>>>(a);
+    B200_CHECK_LAUNCH("fir_tc2_kernel");
+    return B200DSP_OK;
+}
+
+int launch_fir_tc2(const void *x, const void *hist, void *y, int64_t n, int32_t hist_len,
+                   const void *amat_dev, int sb_exp, int ntaps, int tile_rows, int sm_count, cudaStream_t stream)
+{
+    using namespace tc2;
+    Args a;
+    a.x = static_cast<const float2 *>(x);
+    a.hist = static_cast<const float2 *>(hist);
+    a.y = static_cast<float2 *>(y);
+    a.amat = static_cast<const uint4 *>(amat_dev);
+    a.n = n;
+    a.n_tiles = 0;
+    a.hist_len = hist_len;
+    a.sb_exp = sb_exp;
+    // T[c][kk] = b[c + 256 - kk] is non-zero only for kk >= 257 - ntaps: skip the leading all-zero k-blocks
+    a.jmin = (HALO + 1 - ntaps) / BK;
+    if (a.jmin < 0) a.jmin = 0;
+    a.dbg = 0;
+    if (const char *e = getenv("B200DSP_TC_DBG")) a.dbg = atoi(e);
+    if (a.dbg) {
+        if (tile_rows == 128) return launch_tc2_cfg<128, true>(a, n, sm_count, stream);
+        return launch_tc2_cfg<64, true>(a, n, sm_count, stream);
+    }
+    if (tile_rows == 128) return launch_tc2_cfg<128, false>(a, n, sm_count, stream);
+    return launch_tc2_cfg<64, false>(a, n, sm_count, stream);
+}
+
+}  // namespace b200dsp

@@ -23,7 +23,10 @@ class _Pipe:
 
     def __init__(self, dev, dtype, chunk, k1):
         self.k1 = k1
-        self.xbuf = [torch.empty(k1 + chunk, dtype=dtype, device=dev) for _ in range(NBUF)]
+        # the chunk itself starts at a 64-sample boundary so the tensor-core path (16-byte aligned
+        # bulk-TMA loads) is taken; the halo sits right in front of it
+        self.ka = (k1 + 63) // 64 * 64
+        self.xbuf = [torch.empty(self.ka + chunk, dtype=dtype, device=dev) for _ in range(NBUF)]
         self.ybuf = [torch.empty(chunk, dtype=dtype, device=dev) for _ in range(NBUF)]
         self.s_h2d = torch.cuda.Stream(dev)
         self.s_cmp = torch.cuda.Stream(dev)
@@ -56,6 +59,7 @@ def fir_filter_host(plan: _engine.FirPlan, x: torch.Tensor, out=None, chunk: int
         return y
     chunk = max(min(chunk, n), 1)
     p = _pipe(dev, x.dtype, chunk, k1)
+    ka = p.ka
     cur = torch.cuda.current_stream(dev)
     for s in (p.s_h2d, p.s_cmp, p.s_d2h):
         s.wait_stream(cur)
@@ -69,17 +73,17 @@ def fir_filter_host(plan: _engine.FirPlan, x: torch.Tensor, out=None, chunk: int
         with torch.cuda.stream(p.s_h2d):
             if ev_free_x[j] is not None:
                 p.s_h2d.wait_event(ev_free_x[j])
-            xb[k1:k1 + ln].copy_(xs[c0:c0 + ln], non_blocking=True)
+            xb[ka:ka + ln].copy_(xs[c0:c0 + ln], non_blocking=True)
             if c0 > 0 and k1 > 0:
-                xb[:k1].copy_(xs[c0 - k1:c0], non_blocking=True)
+                xb[ka - k1:ka].copy_(xs[c0 - k1:c0], non_blocking=True)
             ev_in = torch.cuda.Event()
             ev_in.record(p.s_h2d)
         with torch.cuda.stream(p.s_cmp):
             p.s_cmp.wait_event(ev_in)
             if ev_free_y[j] is not None:
                 p.s_cmp.wait_event(ev_free_y[j])
-            hist = xb[:k1] if (c0 > 0 and k1 > 0) else None
-            _engine.fir_filter(plan, xb[k1:k1 + ln], hist=hist, out=yb[:ln])
+            hist = xb[ka - k1:ka] if (c0 > 0 and k1 > 0) else None
+            _engine.fir_filter(plan, xb[ka:ka + ln], hist=hist, out=yb[:ln])
             ev_k = torch.cuda.Event()
             ev_k.record(p.s_cmp)
             ev_free_x[j] = ev_k

@@ -9,8 +9,8 @@ complex64 config), no all-reduce / all-gather.  The result is bit-identical to f
 whole stream on one device because the halo reproduces the filter state exactly.
 
 Overlap: the interior outputs ``y[K-1:]`` depend only on local samples, so their kernel is
-launched first; the halo travels meanwhile; the first ``K-1`` outputs are computed by a second,
-tiny launch once the halo has landed.
+launched first; the halo travels meanwhile; the first outputs (up to the next 64-sample boundary
+after ``K-1``) are computed by a second, tiny launch once the halo has landed.
 
 ``halo="peer"`` replaces the NCCL message by a direct NVLink read: the neighbour's tail is
 exposed through symmetric memory and handed to the kernel as its ``hist`` pointer, so the FIR
@@ -101,20 +101,25 @@ class ShardedFIR:
         else:
             halo, works = self.exchange_halo(x_local)
         y = torch.empty_like(x_local)
-        # interior first: needs no halo, overlaps the exchange
-        if n > k1:
-            y[k1:] = self._fir(x_local[k1:], x_local[:k1]) if not on_gpu else \
-                _engine.fir_filter(self.plan, x_local[k1:], hist=x_local[:k1], out=y[k1:])
+        # interior first: needs no halo, overlaps the exchange.  The split point is a multiple of 64
+        # samples so both launches see 16-byte aligned streams (tensor-core path).
+        sp = min((k1 + 63) // 64 * 64, n)
+        if n > sp:
+            hist_i = x_local[sp - k1:sp]
+            if on_gpu:
+                _engine.fir_filter(self.plan, x_local[sp:], hist=hist_i.contiguous(), out=y[sp:])
+            else:
+                y[sp:] = self._fir(x_local[sp:], hist_i)
         if on_gpu:
             cur.wait_event(ev)
         else:
             for w in works:
                 w.wait()
-        head = x_local[:min(k1, n)]
+        head = x_local[:sp]
         if on_gpu:
-            _engine.fir_filter(self.plan, head, hist=halo, out=y[:head.numel()])
+            _engine.fir_filter(self.plan, head, hist=halo, out=y[:sp])
         else:
-            y[:head.numel()] = self._fir(head, halo)
+            y[:sp] = self._fir(head, halo)
         return y
 
     _comm_streams = {}

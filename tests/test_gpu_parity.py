@@ -213,7 +213,7 @@ def test_fir_up_dn_factors(mods, filters, factor):
 def test_fir_halo_equals_monolithic(mods, filters):
     """hist = overlap-save halo: chunked == monolithic.  Bit for bit on the CUDA-core kernels
     (fp64, and complex64 below the tensor-core length threshold); on the tensor-core complex64 path
-    the tile grid moves with the cut, so the fp32 accumulation order changes: equal to 2e-7*max|y|."""
+    the tile grid moves with the cut, so the fp32 accumulation order changes: equal to 1e-6*max|y|."""
     from sk_dsp_comm_b200 import _engine
     b = filters["b256"]
     plan = _engine.FirPlan(b)
@@ -226,7 +226,7 @@ def test_fir_halo_equals_monolithic(mods, filters):
         def same(a, b_):
             if exact:
                 return torch.equal(a, b_)
-            return (a - b_).abs().max().item() <= 4e-7 * scale
+            return (a - b_).abs().max().item() <= 1e-6 * scale      # two fp32 results, each within ~4e-7
 
         for cut in (255, 4096, 17777):
             y2 = _engine.fir_filter(plan, x[cut:].contiguous(), hist=x[cut - 255:cut].contiguous())
@@ -240,6 +240,33 @@ def test_fir_halo_equals_monolithic(mods, filters):
         yd = _engine.fir_dn(plan, x, 4)
         yd2 = _engine.fir_dn(plan, x[cut:].contiguous(), 4, hist=x[cut - 255:cut].contiguous())
         assert torch.equal(yd[cut // 4:], yd2)
+
+
+@pytest.mark.parametrize("ntaps", [1, 2, 63, 64, 65, 101, 128, 129, 192, 193, 255, 256])
+def test_tensor_core_fir_tap_counts(mods, ntaps):
+    """tcgen05 path for every filter length it accepts (<= 256 taps): leading all-zero Toeplitz
+    k-blocks are skipped for short filters.  Also non-symmetric taps and the hist (halo) argument."""
+    from sk_dsp_comm_b200 import _engine
+    rng = np.random.default_rng(ntaps)
+    b = rng.standard_normal(ntaps) / np.sqrt(ntaps)
+    plan = _engine.FirPlan(b)
+    n = 70001
+    x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    xt = torch.from_numpy(x).cuda()
+    mods[2].lib.b200dsp_set_fir_variant(12)
+    try:
+        y = _engine.fir_filter(plan, xt).cpu().numpy()
+        ref = oracle.fir_filter(b, x.astype(np.complex128), backend="c")
+        err, scale = _maxerr(y, ref)
+        assert err <= FIR_TOL32 * scale, (ntaps, err, scale)
+        if ntaps > 1:
+            cut = 4096 * 3
+            hist = xt[cut - (ntaps - 1):cut].contiguous()
+            y2 = _engine.fir_filter(plan, xt[cut:].contiguous(), hist=hist).cpu().numpy()
+            err, scale = _maxerr(y2, ref[cut:])
+            assert err <= FIR_TOL32 * scale, (ntaps, "hist", err, scale)
+    finally:
+        mods[2].lib.b200dsp_set_fir_variant(0)
 
 
 def test_tensor_core_fir_block_scaling(mods, filters):
@@ -403,7 +430,7 @@ def test_cfg2_full_size_windows_and_properties(mods, filters):
     xs[d:] = x[:(1 << 22) - d]
     ys = _engine.fir_filter(plan, xs)
     # (the tensor-core tile grid is anchored at sample 0, so a shift changes the fp32 summation order)
-    assert (ys[d:] - y[:(1 << 22) - d]).abs().max().item() <= 4e-7 * y[:(1 << 22)].abs().max().item()
+    assert (ys[d:] - y[:(1 << 22) - d]).abs().max().item() <= 1e-6 * y[:(1 << 22)].abs().max().item()
     print("cfg2 worst window error / max|y| = %.3g" % worst)
 
 
@@ -468,9 +495,9 @@ def test_host_pipeline_equals_device_path(mods, filters):
     y_host = hostpipe.fir_filter_host(plan, x, chunk=1 << 20)
     y_dev = _engine.fir_filter(plan, x.cuda()).cpu()
     scale = y_dev.abs().max().item()
-    assert (y_host - y_dev).abs().max().item() <= 4e-7 * scale
+    assert (y_host - y_dev).abs().max().item() <= 1e-6 * scale
     y_api = mods[0].multirate_FIR(b).filter(x)          # public API routes long host tensors here
-    assert (y_api - y_dev).abs().max().item() <= 4e-7 * scale
+    assert (y_api - y_dev).abs().max().item() <= 1e-6 * scale
     x64 = torch.randn((1 << 20) + 77, dtype=torch.float64).pin_memory()
     y_host = hostpipe.fir_filter_host(plan, x64, chunk=1 << 18)
     assert torch.equal(y_host, _engine.fir_filter(plan, x64.cuda()).cpu())

@@ -7,7 +7,7 @@ import oracle
 from sk_dsp_comm_b200 import _engine, _cabi
 b = np.load(os.path.join(ROOT, "tests/golden/filters.npz"))["b256"]
 plan = _engine.FirPlan(b)
-_cabi.lib.b200dsp_set_fir_variant(10)
+_cabi.lib.b200dsp_set_fir_variant(int(os.environ.get('B200DSP_VARIANT', '10')))
 what = sys.argv[1]
 if what == "err":
     n = 1 << 21
