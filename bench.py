@@ -147,6 +147,10 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------- GPU arm
 def run_gpu(args):
+    # NCCL / torchrun chatter must not pollute stdout: the contract is ONE JSON line there.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -283,7 +287,8 @@ def run_gpu(args):
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -28,7 +28,9 @@ try:
     torch.cuda.synchronize(); dist.barrier()
     y2 = sh.filter_peer()
     torch.cuda.synchronize(); dist.barrier()
-    print("rank", rank, "peer-halo == nccl-halo:", bool(torch.equal(y, y2)), flush=True)
+    d = (y - y2).abs().max().item() / y.abs().max().item()
+    print("rank", rank, "peer-halo vs nccl-halo max diff / max|y| = %.3g (two fp32 tile grids)" % d, flush=True)
+    assert d <= 1e-6
 except Exception as e:
     print("rank", rank, "peer-halo path unavailable:", repr(e)[:300], flush=True)
 # ---- timing breakdown (why is a sharded step slower than a plain one?) ----
