@@ -161,10 +161,15 @@ struct b200dsp_fir_plan_impl {
     int32_t ntaps;
     float *taps_f32;
     double *taps_f64;
+    double *taps_host;   // host copy (lazy construction of tensor-core tap matrices)
     void *tc_bmat;       // tensor-core path: swizzled fp16 hi/lo Toeplitz tap matrices (or NULL)
     int32_t tc_sb_exp;
     void *tc2_amat;      // taps-stationary tensor-core path: 128 x 320 fp16 matrix for TMEM (or NULL)
     int32_t tc2_sb_exp;
+    // float32 tensor-core paths (fir_tc_real.cu): tap matrices per (mode, factor), built on first use
+    void *tcr_mat[4][5];
+    int32_t tcr_sb[4][5];
+    int8_t tcr_state[4][5];   // 0 not built yet, 1 ready, -1 unsupported for this filter
     int32_t sm_count;
 };
 
@@ -174,6 +179,11 @@ int tc_matrix_bytes();
 int tc_max_taps();
 int launch_fir_tc(const void *x, const void *hist, void *y, int64_t n, int32_t hist_len,
                   const void *bmat_dev, int sb_exp, int bo_mode, int sm_count, cudaStream_t stream);
+// fir_tc_real.cu
+int tcr_build(const double *taps, int ntaps, int mode, int P, unsigned char *out, int *sb_exp);
+int tcr_matrix_bytes(int mode, int P);
+int launch_fir_tc_real(int mode, int P, const void *x, const void *hist, void *y, int64_t n, int32_t hist_len,
+                       const void *amat_dev, int sb_exp, int ntaps, int sm_count, cudaStream_t stream);
 // fir_tc2.cu
 int tc2_build_tap_matrix(const double *taps, int ntaps, unsigned char *out, int *sb_exp);
 int tc2_matrix_bytes();
@@ -262,13 +272,47 @@ static int launch_fir_fit(const b200dsp_fir_plan_impl *p, const void *x, const v
     return rc;
 }
 
+// Lazily build (and cache in the plan) the TMEM tap matrices of one float32 tensor-core mode.
+static bool tcr_ready(b200dsp_fir_plan_impl *p, int mode, int P)
+{
+    if (p->tcr_state[mode][P] == 0) {
+        p->tcr_state[mode][P] = -1;
+        const int nb = tcr_matrix_bytes(mode, P);
+        unsigned char *hb = new unsigned char[nb];
+        int sb = 0;
+        if (tcr_build(p->taps_host, p->ntaps, mode, P, hb, &sb) == 0) {
+            void *d = nullptr;
+            if (cudaMalloc(&d, nb) == cudaSuccess &&
+                cudaMemcpy(d, hb, nb, cudaMemcpyHostToDevice) == cudaSuccess) {
+                p->tcr_mat[mode][P] = d;
+                p->tcr_sb[mode][P] = sb;
+                p->tcr_state[mode][P] = 1;
+            } else if (d) {
+                cudaFree(d);
+            }
+        }
+        delete[] hb;
+    }
+    return p->tcr_state[mode][P] == 1;
+}
+
 static int fir_dispatch(const b200dsp_fir_plan_impl *p, int dtype, const void *x, const void *hist,
                         void *y, int64_t n, int64_t n_m, int32_t L, int32_t M, int32_t hist_len,
                         cudaStream_t s)
 {
     const int v = g_fir_variant;
     switch (dtype) {
-    case B200DSP_F32:
+    case B200DSP_F32: {
+        // float32 streams on the tensor cores (fir_tc_real.cu): filter (<= 256 taps), up/dn by 2..4 with at
+        // most 64 taps per phase; 16-byte aligned streams only.  v == 9 forces the CUDA-core kernel.
+        const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+        const int mode = (L > 1) ? 2 : (M > 1 ? 3 : 1);
+        const int P = (L > 1) ? L : (M > 1 ? M : 1);
+        if (v == 0 && aligned && P <= 4 && n_m >= 16384 &&
+            tcr_ready(const_cast<b200dsp_fir_plan_impl *>(p), mode, P))
+            return launch_fir_tc_real(mode, P, x, hist, y, n, hist_len, p->tcr_mat[mode][P],
+                                      p->tcr_sb[mode][P], p->ntaps, p->sm_count, s);
+        }
         if (v == 1) return launch_fir_fit<float, 16>(p, x, hist, y, n, n_m, L, M, hist_len, s, 256);
         return launch_fir_fit<float, 32>(p, x, hist, y, n, n_m, L, M, hist_len, s, 128);
     case B200DSP_C64:
@@ -325,6 +369,11 @@ int b200dsp_fir_plan_create(const double *taps_host, int32_t ntaps, b200dsp_fir_
     p->tc_sb_exp = 0;
     p->tc2_amat = nullptr;
     p->tc2_sb_exp = 0;
+    memset(p->tcr_mat, 0, sizeof(p->tcr_mat));
+    memset(p->tcr_sb, 0, sizeof(p->tcr_sb));
+    memset(p->tcr_state, 0, sizeof(p->tcr_state));
+    p->taps_host = new double[ntaps];
+    memcpy(p->taps_host, taps_host, sizeof(double) * ntaps);
     p->sm_count = 148;
     {
         int dev = 0;
@@ -362,6 +411,7 @@ int b200dsp_fir_plan_create(const double *taps_host, int32_t ntaps, b200dsp_fir_
         cudaFree(p->taps_f64);
         cudaFree(p->tc_bmat);
         cudaFree(p->tc2_amat);
+        delete[] p->taps_host;
         delete p;
         return B200DSP_E_CUDA;
     }
@@ -376,6 +426,9 @@ void b200dsp_fir_plan_destroy(b200dsp_fir_plan *plan)
     cudaFree(plan->taps_f64);
     cudaFree(plan->tc_bmat);
     cudaFree(plan->tc2_amat);
+    for (int m = 0; m < 4; ++m)
+        for (int q = 0; q < 5; ++q) cudaFree(plan->tcr_mat[m][q]);
+    delete[] plan->taps_host;
     delete plan;
 }
 

@@ -269,6 +269,39 @@ def test_tensor_core_fir_tap_counts(mods, ntaps):
         mods[2].lib.b200dsp_set_fir_variant(0)
 
 
+@pytest.mark.parametrize("fname", ["b256", "b101", "b33_remez_bpf", "b7", "b1"])
+def test_tensor_core_f32_filter_up_dn(mods, filters, fname):
+    """float32 streams long enough for the tcgen05 kernels (fir_tc_real.cu): filter, up(2..4), dn(2..4);
+    combinations the tensor-core path cannot take (too many taps per phase) silently use the CUDA cores."""
+    from sk_dsp_comm_b200 import _engine
+    b = filters[fname]
+    plan = _engine.FirPlan(b)
+    rng = np.random.default_rng(len(b))
+    for n in (70001, 262144 + 5):
+        x = rng.standard_normal(n).astype(np.float32)
+        x64 = x.astype(np.float64)
+        xt = torch.from_numpy(x).cuda()
+        err, scale = _maxerr(_engine.fir_filter(plan, xt).cpu().numpy(), oracle.fir_filter(b, x64, backend="c"))
+        assert err <= FIR_TOL32 * scale, (fname, n, "filter", err, scale)
+        for F in (2, 3, 4):
+            err, scale = _maxerr(_engine.fir_up(plan, xt, F).cpu().numpy(), oracle.fir_up(b, x64, F, backend="c"))
+            assert err <= FIR_TOL32 * scale, (fname, n, "up", F, err, scale)
+            err, scale = _maxerr(_engine.fir_dn(plan, xt, F).cpu().numpy(), oracle.fir_dn(b, x64, F, backend="c"))
+            assert err <= FIR_TOL32 * scale, (fname, n, "dn", F, err, scale)
+    # halo argument on the tensor-core paths (cuts on tile boundaries keep the tile grid: bit identical)
+    x = torch.randn(300000, dtype=torch.float32, device="cuda")
+    cut = 65536
+    if len(b) > 1:
+        k1 = len(b) - 1
+        y = _engine.fir_filter(plan, x)
+        assert torch.equal(y[cut:], _engine.fir_filter(plan, x[cut:].contiguous(), hist=x[cut - k1:cut].contiguous()))
+        hl = plan.up_hist_len(4)
+        yu = _engine.fir_up(plan, x, 4)
+        assert torch.equal(yu[4 * cut:], _engine.fir_up(plan, x[cut:].contiguous(), 4, hist=x[cut - hl:cut].contiguous()))
+        yd = _engine.fir_dn(plan, x, 4)
+        assert torch.equal(yd[cut // 4:], _engine.fir_dn(plan, x[cut:].contiguous(), 4, hist=x[cut - k1:cut].contiguous()))
+
+
 def test_tensor_core_fir_block_scaling(mods, filters):
     """The tcgen05 path splits fp32 into fp16 hi/lo around a per-tile power-of-two scale: results
     must be scale invariant (1e-30 .. 1e30), survive tiles that are all zero, and handle a stream
