@@ -3,43 +3,34 @@
 // Replaces scipy.signal.sosfilt as called by the reference's multirate_IIR
 // (src/sk_dsp_comm/multirate_helper.py:169-192).  sosfilt is a strictly sequential
 // direct-form-II-transposed loop; here the same recurrence is evaluated in
-// three launches per group of <= 8 sections:
+// three launches per group of <= 8 sections.  The cascade is LTI (s[n+1] = A s[n] + B x[n]), so only
+// state VECTORS are ever scanned, with constant host-computed matrices A^(256 * 2^j):
 //
-//   K1 sos_pass1   one block per tile of T = SOS_NT*LC samples.  The tile is staged in shared
-//                  memory TRANSPOSED (sample n of chunk t at [n][t]) so that thread t can walk
-//                  its own LC-sample chunk with conflict-free accesses.  Each thread runs the
-//                  cascade over its chunk from ZERO state and keeps the 2*nsec final state
-//                  values ("chunk carry").  A Kogge-Stone scan over the SOS_NT carries with the
-//                  constant matrices A^(LC*2^j) (the cascade is LTI, so only state VECTORS are
-//                  scanned, never matrices) yields the tile carry.  Chunk carries and the
-//                  tile carry go to the workspace.
-//   K2 sos_tile_scan   one block: scans the tile carries with A^T (runs of r tiles per
-//                  thread + Kogge-Stone over the runs) -> true state at every tile start.
-//   K3 sos_pass2   one block per tile: re-loads the tile, scans the stored chunk carries
-//                  with the tile's true start state folded in, then every thread re-runs the
-//                  cascade over its chunk from its TRUE start state and writes the outputs
-//                  (through the same transposed tile -> coalesced stores).
+//   K1 sos_pass1   every thread streams its own chunk of 256 consecutive samples straight from global
+//                  memory (128-bit loads; the 32 lanes of a warp walk 32 different 128-byte lines, L1 keeps
+//                  the lines between a thread's consecutive loads -- no shared-memory staging, no
+//                  transposition, DRAM sectors fully used) and runs the cascade from ZERO state: the
+//                  2*nsec final state values are the "chunk carry".  A block-wide Kogge-Stone scan over
+//                  the 256 carries of a tile (65536 samples) yields the tile carry.
+//   K2 sos_tile_scan   one block: scans the tile carries with A^65536 (runs of tiles per thread +
+//                  Kogge-Stone over the runs) -> true state at every tile start (fp64).
+//   K3 sos_pass2   rescans the stored chunk carries with the tile's true start state folded in, then
+//                  every thread re-runs the cascade over its chunk from its TRUE start state and streams
+//                  the outputs back with 128-bit stores.
 //
-// Up-sampling (zero stuffing, x L gain) is fused into the tile load and down-sampling into
-// the tile store, so multirate_IIR.up/.dn never materialise the full-rate stream.
+// Up-sampling (zero stuffing, x L gain) is fused into the chunk read and down-sampling into the
+// write (element-wise path), so multirate_IIR.up/.dn never materialise the full-rate stream.
 #include "common.cuh"
 #include <vector>
 
 namespace b200dsp {
 
-constexpr int SOS_NT = 256;          // threads per block in K1/K3 (256 -> 2-3 resident blocks/SM so
-                                     // one block's tile load overlaps another block's recurrence)
+constexpr int SOS_NT = 256;          // threads per block = chunks per tile
 constexpr int SOS_LEVELS = 8;        // log2(SOS_NT)
+constexpr int SOS_LC = 256;          // samples per chunk (one thread)
 constexpr int SOS_MAXSEC = 8;        // sections per launch group
 constexpr int SOS_K2_NT = 256;       // threads in the tile-scan block
 constexpr int SOS_K2_LEVELS = 8;
-
-template <typename S> struct SosCfg;
-template <> struct SosCfg<float>   { static constexpr int LC = 64; static constexpr int LCI = 2; };
-template <> struct SosCfg<double>  { static constexpr int LC = 32; static constexpr int LCI = 1; };
-template <> struct SosCfg<float2>  { static constexpr int LC = 32; static constexpr int LCI = 1; };
-template <> struct SosCfg<double2> { static constexpr int LC = 16; static constexpr int LCI = 0; };
-// LCI indexes the plan's per-LC matrix sets: LC = 16 << LCI
 
 template <typename C, int NSEC> struct SosCoef { C c[NSEC][5]; };   // b0 b1 b2 -a1 -a2
 
@@ -120,39 +111,34 @@ struct SosArgs {
     SosCoef<C, NSEC> k;
 };
 
-template <typename S, int LC>
-__device__ __forceinline__ int tile_addr(int v) { return (v & (LC - 1)) * (SOS_NT + 1) + (v / LC); }
-
+// ---- streaming access to one thread's chunk -----------------------------------------------------
+// Input element of filter-rate index g (fused zero stuffing for L > 1).
 template <typename S, int NSEC>
-__device__ void sos_load_tile(S *tile, const SosArgs<S, NSEC> &a, int64_t tile0, int tid)
-{
+struct ChunkReader {
     using C = typename Sample<S>::C;
-    constexpr int LC = SosCfg<S>::LC;
-    constexpr int T = SOS_NT * LC;
-    if (a.L == 1) {
-        for (int v = tid; v < T; v += SOS_NT) {
-            int64_t g = tile0 + v;
-            S val = zero_of(S());
-            if (g < a.n_rate) val = a.x[g];
-            tile[tile_addr<S, LC>(v)] = val;
-        }
-    } else {
-        const int L = a.L;
-        int64_t g0 = tile0 + tid;
-        int64_t q = g0 / L;
-        int r = (int)(g0 - q * L);
-        const int dq = SOS_NT / L, dr = SOS_NT - dq * L;
-        const C gain = (C)L;
-        for (int v = tid; v < T; v += SOS_NT) {
-            S val = zero_of(S());
-            if (r == 0 && q < a.n_in) val = scale_of(a.x[q], gain);
-            tile[tile_addr<S, LC>(v)] = val;
-            q += dq;
-            r += dr;
-            if (r >= L) { r -= L; ++q; }
-        }
+    const SosArgs<S, NSEC> &a;
+    int64_t q;     // input index of the current filter-rate sample (L > 1)
+    int r;         // phase within the zero-stuffing period
+    __device__ ChunkReader(const SosArgs<S, NSEC> &a_, int64_t g0) : a(a_) {
+        q = (a.L == 1) ? g0 : g0 / a.L;
+        r = (a.L == 1) ? 0 : (int)(g0 - q * a.L);
     }
-}
+    __device__ __forceinline__ S next(int64_t g) {
+        S v = zero_of(S());
+        if (a.L == 1) {
+            if (g < a.n_rate) v = a.x[g];
+        } else {
+            if (r == 0 && q < a.n_in) v = scale_of(a.x[q], (C)a.L);
+            if (++r == a.L) { r = 0; ++q; }
+        }
+        return v;
+    }
+};
+
+template <typename S> struct VecOf {
+    static constexpr int V = 16 / (int)sizeof(S);
+    struct __align__(16) T { S v[16 / sizeof(S)]; };
+};
 
 template <typename S, int NSEC>
 __global__ void __launch_bounds__(SOS_NT) sos_pass1_kernel(const SosArgs<S, NSEC> a)
@@ -160,29 +146,53 @@ __global__ void __launch_bounds__(SOS_NT) sos_pass1_kernel(const SosArgs<S, NSEC
     using C = typename Sample<S>::C;
     constexpr int NCH = Sample<S>::NCH;
     constexpr int D = 2 * NSEC;
-    constexpr int LC = SosCfg<S>::LC;
-    constexpr int T = SOS_NT * LC;
+    constexpr int V = VecOf<S>::V;
+    using Vec = typename VecOf<S>::T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    S *tile = reinterpret_cast<S *>(smem_raw);
-    C *mats = reinterpret_cast<C *>(smem_raw + sizeof(S) * (size_t)LC * (SOS_NT + 1));
-    C *xch = reinterpret_cast<C *>(smem_raw);      // aliases the tile (dead after the chunk pass)
+    C *mats = reinterpret_cast<C *>(smem_raw);
+    C *xch = mats + SOS_LEVELS * D * D;
     const int tid = threadIdx.x;
-    const int64_t tile0 = (int64_t)blockIdx.x * T;
+    const int64_t g0 = ((int64_t)blockIdx.x * SOS_NT + tid) * SOS_LC;
 
     for (int i = tid; i < SOS_LEVELS * D * D; i += SOS_NT) mats[i] = a.mats[i];
-    sos_load_tile<S, NSEC>(tile, a, tile0, tid);
-    __syncthreads();
 
     C z[NCH][D];
 #pragma unroll
     for (int c = 0; c < NCH; ++c)
 #pragma unroll
         for (int d = 0; d < D; ++d) z[c][d] = (C)0;
-#pragma unroll 4
-    for (int n = 0; n < LC; ++n) {
-        S v = tile[n * (SOS_NT + 1) + tid];
+
+    const bool fast = (a.L == 1) && (g0 + SOS_LC <= a.n_rate) && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0);
+    if (fast) {
+        const Vec *px = reinterpret_cast<const Vec *>(a.x + g0);
+        constexpr int NB = SOS_LC / V, PF = 4;           // vectors per chunk, prefetch depth
+        Vec cur[PF];
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) sos_step<C, NSEC>(a.k, z[c], ch_get(v, c));
+        for (int k = 0; k < PF; ++k) cur[k] = px[k];
+#pragma unroll 1
+        for (int b = 0; b < NB; b += PF) {
+            Vec nxt[PF];
+            if (b + PF < NB) {
+#pragma unroll
+                for (int k = 0; k < PF; ++k) nxt[k] = px[b + PF + k];
+            }
+#pragma unroll
+            for (int k = 0; k < PF; ++k)
+#pragma unroll
+                for (int e = 0; e < V; ++e)
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) sos_step<C, NSEC>(a.k, z[c], ch_get(cur[k].v[e], c));
+#pragma unroll
+            for (int k = 0; k < PF; ++k) cur[k] = nxt[k];
+        }
+    } else if (g0 < a.n_rate) {
+        ChunkReader<S, NSEC> rd(a, g0);
+#pragma unroll 1
+        for (int i = 0; i < SOS_LC; ++i) {
+            const S v = rd.next(g0 + i);
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) sos_step<C, NSEC>(a.k, z[c], ch_get(v, c));
+        }
     }
     // chunk carries -> workspace (coalesced over tid)
     C *cw = a.carry + (size_t)blockIdx.x * NCH * D * SOS_NT;
@@ -190,6 +200,7 @@ __global__ void __launch_bounds__(SOS_NT) sos_pass1_kernel(const SosArgs<S, NSEC
     for (int c = 0; c < NCH; ++c)
 #pragma unroll
         for (int d = 0; d < D; ++d) cw[(c * D + d) * SOS_NT + tid] = z[c][d];
+    __syncthreads();                                   // mats staged
     // tile carry = last element of the inclusive scan
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
@@ -207,17 +218,15 @@ __global__ void __launch_bounds__(SOS_NT) sos_pass2_kernel(const SosArgs<S, NSEC
     using C = typename Sample<S>::C;
     constexpr int NCH = Sample<S>::NCH;
     constexpr int D = 2 * NSEC;
-    constexpr int LC = SosCfg<S>::LC;
-    constexpr int T = SOS_NT * LC;
+    constexpr int V = VecOf<S>::V;
+    using Vec = typename VecOf<S>::T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    S *tile = reinterpret_cast<S *>(smem_raw);
-    C *mats = reinterpret_cast<C *>(smem_raw + sizeof(S) * (size_t)LC * (SOS_NT + 1));
+    C *mats = reinterpret_cast<C *>(smem_raw);
     C *xch = mats + SOS_LEVELS * D * D;
     const int tid = threadIdx.x;
-    const int64_t tile0 = (int64_t)blockIdx.x * T;
+    const int64_t g0 = ((int64_t)blockIdx.x * SOS_NT + tid) * SOS_LC;
 
     for (int i = tid; i < SOS_LEVELS * D * D; i += SOS_NT) mats[i] = a.mats[i];
-    sos_load_tile<S, NSEC>(tile, a, tile0, tid);
 
     C z[NCH][D];
     const C *cw = a.carry + (size_t)blockIdx.x * NCH * D * SOS_NT;
@@ -242,36 +251,58 @@ __global__ void __launch_bounds__(SOS_NT) sos_pass2_kernel(const SosArgs<S, NSEC
         for (int d = 0; d < D; ++d) z[c][d] = (tid == 0) ? s0[d] : xch[d * SOS_NT + tid - 1];
     }
 
-    // corrected pass: true start state -> outputs, in place in the tile
-    const int64_t last = a.n_rate - 1 - tile0 - (int64_t)tid * LC;    // position of the final sample
-#pragma unroll 4
-    for (int n = 0; n < LC; ++n) {
-        S v = tile[n * (SOS_NT + 1) + tid];
-        S o;
+    // corrected pass: true start state -> outputs
+    const int64_t last = a.n_rate - 1 - g0;            // position of the stream's final sample in this chunk
+    const bool fast = (a.L == 1) && (a.M == 1) && (g0 + SOS_LC <= a.n_rate) && (a.zf == nullptr || last >= SOS_LC || last < 0) &&
+                      (((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.y)) & 15) == 0);
+    if (fast) {
+        const Vec *px = reinterpret_cast<const Vec *>(a.x + g0);
+        Vec *py = reinterpret_cast<Vec *>(a.y + g0);
+        constexpr int NB = SOS_LC / V, PF = 4;
+        Vec cur[PF];
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) ch_set(o, c, sos_step<C, NSEC>(a.k, z[c], ch_get(v, c)));
-        tile[n * (SOS_NT + 1) + tid] = o;
-        if (a.zf != nullptr && n == last) {
+        for (int k = 0; k < PF; ++k) cur[k] = px[k];
+#pragma unroll 1
+        for (int b = 0; b < NB; b += PF) {
+            Vec nxt[PF];
+            if (b + PF < NB) {
 #pragma unroll
-            for (int c = 0; c < NCH; ++c)
+                for (int k = 0; k < PF; ++k) nxt[k] = px[b + PF + k];
+            }
 #pragma unroll
-                for (int d = 0; d < D; ++d)
-                    if (d < a.d_real) a.zf[d * NCH + c] = z[c][d];
+            for (int k = 0; k < PF; ++k) {
+                Vec o;
+#pragma unroll
+                for (int e = 0; e < V; ++e)
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) ch_set(o.v[e], c, sos_step<C, NSEC>(a.k, z[c], ch_get(cur[k].v[e], c)));
+                py[b + k] = o;
+            }
+#pragma unroll
+            for (int k = 0; k < PF; ++k) cur[k] = nxt[k];
         }
-    }
-    __syncthreads();
-    if (a.M == 1) {
-        for (int v = tid; v < T; v += SOS_NT) {
-            int64_t g = tile0 + v;
-            if (g < a.n_out) a.y[g] = tile[tile_addr<S, LC>(v)];
-        }
-    } else {
-        const int M = a.M;
-        int64_t o = (tile0 + M - 1) / M + tid;
-        for (;; o += SOS_NT) {
-            int64_t g = o * M;
-            if (g >= tile0 + T || o >= a.n_out) break;
-            a.y[o] = tile[tile_addr<S, LC>((int)(g - tile0))];
+    } else if (g0 < a.n_rate) {
+        ChunkReader<S, NSEC> rd(a, g0);
+        // fused decimation: output index / phase of the current filter-rate sample
+        int64_t mo = (a.M == 1) ? g0 : g0 / a.M;
+        int mr = (a.M == 1) ? 0 : (int)(g0 - mo * a.M);
+#pragma unroll 1
+        for (int i = 0; i < SOS_LC; ++i) {
+            const int64_t g = g0 + i;
+            if (g >= a.n_rate) break;
+            const S v = rd.next(g);
+            S o;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) ch_set(o, c, sos_step<C, NSEC>(a.k, z[c], ch_get(v, c)));
+            if (mr == 0 && mo < a.n_out) a.y[mo] = o;
+            if (a.M == 1) { ++mo; } else if (++mr == a.M) { mr = 0; ++mo; }
+            if (a.zf != nullptr && i == last) {
+#pragma unroll
+                for (int c = 0; c < NCH; ++c)
+#pragma unroll
+                    for (int d = 0; d < D; ++d)
+                        if (d < a.d_real) a.zf[d * NCH + c] = z[c][d];
+            }
         }
     }
 }
@@ -354,9 +385,9 @@ struct SosGroup {
     int nsec_real;                     // sections that came from the user's sos
     double coef[SOS_MAXSEC][5];        // b0 b1 b2 -a1 -a2
     std::vector<double> A;             // D x D one-sample state transition
-    std::vector<double> tileA[3];      // A^(SOS_NT*LC) for LC = 16,32,64
-    float *mats_f32[3];                // device [SOS_LEVELS][D*D], per LC
-    double *mats_f64[3];
+    std::vector<double> tileA;         // A^(SOS_NT*SOS_LC): one tile step
+    float *mats_f32;                   // device [SOS_LEVELS][D*D]: A^(SOS_LC * 2^j)
+    double *mats_f64;
 };
 
 struct b200dsp_sos_plan_impl {
@@ -396,9 +427,7 @@ static int run_group(const SosGroup &g, const S *x, S *y, int64_t n_in, int64_t 
     using C = typename Sample<S>::C;
     constexpr int NCH = Sample<S>::NCH;
     constexpr int D = 2 * NSEC;
-    constexpr int LC = SosCfg<S>::LC;
-    constexpr int LCI = SosCfg<S>::LCI;
-    constexpr int64_t T = (int64_t)SOS_NT * LC;
+    constexpr int64_t T = (int64_t)SOS_NT * SOS_LC;
     const int64_t n_tiles = (n_rate + T - 1) / T;
     if (n_tiles > 2147483647LL) {
         set_error("sos: too many tiles");
@@ -412,8 +441,8 @@ static int run_group(const SosGroup &g, const S *x, S *y, int64_t n_in, int64_t 
     a.n_out = n_out;
     a.L = L;
     a.M = M;
-    a.mats = sizeof(C) == 4 ? reinterpret_cast<const C *>(g.mats_f32[LCI])
-                            : reinterpret_cast<const C *>(g.mats_f64[LCI]);
+    a.mats = sizeof(C) == 4 ? reinterpret_cast<const C *>(g.mats_f32)
+                            : reinterpret_cast<const C *>(g.mats_f64);
     size_t per_tile = (size_t)NCH * D * sizeof(C);
     size_t off = 0;
     a.aggr = reinterpret_cast<C *>(ws + off);
@@ -426,16 +455,9 @@ static int run_group(const SosGroup &g, const S *x, S *y, int64_t n_in, int64_t 
     for (int s = 0; s < NSEC; ++s)
         for (int q = 0; q < 5; ++q) a.k.c[s][q] = (C)g.coef[s][q];
 
-    const size_t tile_bytes = sizeof(S) * (size_t)LC * (SOS_NT + 1);
     const size_t mats_bytes = sizeof(C) * (size_t)SOS_LEVELS * D * D;
     const size_t xch_bytes = sizeof(C) * (size_t)SOS_NT * D;
-    size_t smem1 = tile_bytes + mats_bytes;
-    if (smem1 < xch_bytes) smem1 = xch_bytes;          // xch aliases the tile in K1
-    size_t smem3 = tile_bytes + mats_bytes + xch_bytes;
-    if (smem3 > kMaxSmemPerBlock) {
-        set_error("sos: shared-memory budget exceeded (%zu B)", smem3);
-        return B200DSP_E_UNSUPPORTED;
-    }
+    const size_t smem1 = mats_bytes + xch_bytes, smem3 = smem1;
     auto k1 = sos_pass1_kernel<S, NSEC>;
     auto k3 = sos_pass2_kernel<S, NSEC>;
     B200_CHECK_CUDA(allow_smem(k1, smem1));
@@ -447,9 +469,9 @@ static int run_group(const SosGroup &g, const S *x, S *y, int64_t n_in, int64_t 
     // tile-level scan matrices: m1 = A^T, pj = (A^T)^(run*2^j)
     TileScanMats<D> mm;
     const int64_t run = (n_tiles + SOS_K2_NT - 1) / SOS_K2_NT;
-    memcpy(mm.m1, g.tileA[LCI].data(), sizeof(double) * D * D);
+    memcpy(mm.m1, g.tileA.data(), sizeof(double) * D * D);
     std::vector<double> p;
-    matpow(g.tileA[LCI], run, p, D);
+    matpow(g.tileA, run, p, D);
     for (int j = 0; j < SOS_K2_LEVELS; ++j) {
         memcpy(mm.pj[j], p.data(), sizeof(double) * D * D);
         if (j + 1 < SOS_K2_LEVELS) matmul(p, p, p, D);
@@ -494,7 +516,7 @@ static size_t dtype_size(int dtype)
 // workspace = [scan area (aggr, start, carry) for the largest group] [tmp stream if >1 group]
 static size_t sos_scan_area_bytes(int dtype, int64_t n_rate)
 {
-    const int lc = dtype == B200DSP_F32 ? 64 : (dtype == B200DSP_C128 ? 16 : 32);
+    const int lc = SOS_LC;
     const int nch = (dtype == B200DSP_C64 || dtype == B200DSP_C128) ? 2 : 1;
     const size_t csz = (dtype == B200DSP_F32 || dtype == B200DSP_C64) ? 4 : 8;
     const int64_t T = (int64_t)SOS_NT * lc;
@@ -584,26 +606,23 @@ int b200dsp_sos_plan_create(const double *sos_host, int32_t nsec, b200dsp_sos_pl
             }
             for (int i = 0; i < D; ++i) g.A[i * D + d] = z[i];
         }
-        for (int li = 0; li < 3; ++li) {
-            g.mats_f32[li] = nullptr;
-            g.mats_f64[li] = nullptr;
-        }
+        g.mats_f32 = nullptr;
+        g.mats_f64 = nullptr;
         cudaError_t e = cudaSuccess;
-        for (int li = 0; li < 3 && e == cudaSuccess; ++li) {
-            const int lc = 16 << li;
+        {
             std::vector<double> pw;
-            matpow(g.A, lc, pw, D);
+            matpow(g.A, SOS_LC, pw, D);
             std::vector<double> all((size_t)SOS_LEVELS * D * D);
             for (int j = 0; j < SOS_LEVELS; ++j) {
                 memcpy(all.data() + (size_t)j * D * D, pw.data(), sizeof(double) * D * D);
                 matmul(pw, pw, pw, D);
             }
-            g.tileA[li] = pw;       // A^(lc * SOS_NT)
+            g.tileA = pw;           // A^(SOS_LC * SOS_NT)
             std::vector<float> allf(all.begin(), all.end());
-            e = cudaMalloc(&g.mats_f32[li], allf.size() * sizeof(float));
-            if (e == cudaSuccess) e = cudaMalloc(&g.mats_f64[li], all.size() * sizeof(double));
-            if (e == cudaSuccess) e = cudaMemcpy(g.mats_f32[li], allf.data(), allf.size() * sizeof(float), cudaMemcpyHostToDevice);
-            if (e == cudaSuccess) e = cudaMemcpy(g.mats_f64[li], all.data(), all.size() * sizeof(double), cudaMemcpyHostToDevice);
+            e = cudaMalloc(&g.mats_f32, allf.size() * sizeof(float));
+            if (e == cudaSuccess) e = cudaMalloc(&g.mats_f64, all.size() * sizeof(double));
+            if (e == cudaSuccess) e = cudaMemcpy(g.mats_f32, allf.data(), allf.size() * sizeof(float), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(g.mats_f64, all.data(), all.size() * sizeof(double), cudaMemcpyHostToDevice);
         }
         p->groups.push_back(g);
         if (e != cudaSuccess) {
@@ -619,11 +638,10 @@ int b200dsp_sos_plan_create(const double *sos_host, int32_t nsec, b200dsp_sos_pl
 void b200dsp_sos_plan_destroy(b200dsp_sos_plan *plan)
 {
     if (!plan) return;
-    for (auto &g : plan->groups)
-        for (int li = 0; li < 3; ++li) {
-            cudaFree(g.mats_f32[li]);
-            cudaFree(g.mats_f64[li]);
-        }
+    for (auto &g : plan->groups) {
+        cudaFree(g.mats_f32);
+        cudaFree(g.mats_f64);
+    }
     delete plan;
 }
 

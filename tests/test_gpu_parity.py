@@ -336,7 +336,7 @@ def test_tensor_core_fir_block_scaling(mods, filters):
     assert (y_cc - y1).abs().max().item() <= 1.5e-6 * scale
 
 
-@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 4095, 4096, 4097, 16383, 16384, 16385, 32769, 100003])
+@pytest.mark.parametrize("n", [1, 2, 255, 256, 257, 4097, 65535, 65536, 65537, 131073, 200003])
 @pytest.mark.parametrize("dt", ["float32", "complex64", "float64", "complex128"])
 def test_sos_sizes_across_tile_boundaries(mods, filters, n, dt):
     rng = np.random.default_rng(n + 3)
