@@ -162,8 +162,6 @@ struct b200dsp_fir_plan_impl {
     float *taps_f32;
     double *taps_f64;
     double *taps_host;   // host copy (lazy construction of tensor-core tap matrices)
-    void *tc_bmat;       // tensor-core path: swizzled fp16 hi/lo Toeplitz tap matrices (or NULL)
-    int32_t tc_sb_exp;
     void *tc2_amat;      // taps-stationary tensor-core path: 128 x 320 fp16 matrix for TMEM (or NULL)
     int32_t tc2_sb_exp;
     // float32 tensor-core paths (fir_tc_real.cu): tap matrices per (mode, factor), built on first use
@@ -173,12 +171,6 @@ struct b200dsp_fir_plan_impl {
     int32_t sm_count;
 };
 
-// fir_tc.cu
-int tc_build_tap_matrices(const double *taps, int ntaps, unsigned char *out, int *sb_exp);
-int tc_matrix_bytes();
-int tc_max_taps();
-int launch_fir_tc(const void *x, const void *hist, void *y, int64_t n, int32_t hist_len,
-                  const void *bmat_dev, int sb_exp, int bo_mode, int sm_count, cudaStream_t stream);
 // fir_tc_real.cu
 int tcr_build(const double *taps, int ntaps, int mode, int P, unsigned char *out, int *sb_exp);
 int tcr_matrix_bytes(int mode, int P);
@@ -320,15 +312,13 @@ static int fir_dispatch(const b200dsp_fir_plan_impl *p, int dtype, const void *x
         // v == 10 forces it for any length, v == 9 forces the CUDA-core kernel.
         // Long complex64 streams: block-Toeplitz GEMM on the tensor cores (fir_tc2.cu, taps in TMEM).
         // Needs 16-byte aligned streams (bulk TMA in, vector stores out); otherwise the CUDA-core kernel.
-        //   v == 0 auto | 12 force tc2 (64-row tiles) | 13 tc2 (128-row tiles) | 10 first-generation fir_tc.cu
+        //   v == 0 auto | 12 / 14 / 13 force the tensor-core kernel with 64 / 96 / 128-row tiles
         //   | 9 force CUDA cores | 1..5 CUDA-core shapes
         if (L == 1 && M == 1) {
             const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
-            if (p->tc2_amat != nullptr && (v == 12 || v == 13 || (v == 0 && n >= 32768 && aligned)))
+            if (p->tc2_amat != nullptr && (v == 12 || v == 13 || v == 14 || (v == 0 && n >= 32768 && aligned)))
                 return launch_fir_tc2(x, hist, y, n, hist_len, p->tc2_amat, p->tc2_sb_exp, p->ntaps,
-                                      v == 13 ? 128 : 64, p->sm_count, s);
-            if (p->tc_bmat != nullptr && v == 10)
-                return launch_fir_tc(x, hist, y, n, hist_len, p->tc_bmat, p->tc_sb_exp, 0, p->sm_count, s);
+                                      v == 13 ? 128 : (v == 14 ? 96 : 64), p->sm_count, s);
         }
         if (v == 1) return launch_fir_fit<float2, 16>(p, x, hist, y, n, n_m, L, M, hist_len, s, 256);
         if (v == 2) return launch_fir_fit<float2, 16>(p, x, hist, y, n, n_m, L, M, hist_len, s, 128);
@@ -365,8 +355,6 @@ int b200dsp_fir_plan_create(const double *taps_host, int32_t ntaps, b200dsp_fir_
     p->ntaps = ntaps;
     p->taps_f32 = nullptr;
     p->taps_f64 = nullptr;
-    p->tc_bmat = nullptr;
-    p->tc_sb_exp = 0;
     p->tc2_amat = nullptr;
     p->tc2_sb_exp = 0;
     memset(p->tcr_mat, 0, sizeof(p->tcr_mat));
@@ -387,29 +375,19 @@ int b200dsp_fir_plan_create(const double *taps_host, int32_t ntaps, b200dsp_fir_
     if (e == cudaSuccess) e = cudaMemcpy(p->taps_f32, tmp, sizeof(float) * ntaps, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(p->taps_f64, taps_host, sizeof(double) * ntaps, cudaMemcpyHostToDevice);
     delete[] tmp;
-    if (e == cudaSuccess && ntaps <= tc_max_taps()) {
-        const int nb = tc_matrix_bytes();
-        unsigned char *hb = new unsigned char[nb];
-        if (tc_build_tap_matrices(taps_host, ntaps, hb, &p->tc_sb_exp) == 0) {
-            e = cudaMalloc(&p->tc_bmat, nb);
-            if (e == cudaSuccess) e = cudaMemcpy(p->tc_bmat, hb, nb, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && ntaps <= 256) {
+        const int nb2 = tc2_matrix_bytes();
+        unsigned char *h2 = new unsigned char[nb2];
+        if (tc2_build_tap_matrix(taps_host, ntaps, h2, &p->tc2_sb_exp) == 0) {
+            e = cudaMalloc(&p->tc2_amat, nb2);
+            if (e == cudaSuccess) e = cudaMemcpy(p->tc2_amat, h2, nb2, cudaMemcpyHostToDevice);
         }
-        delete[] hb;
-        if (e == cudaSuccess) {
-            const int nb2 = tc2_matrix_bytes();
-            unsigned char *h2 = new unsigned char[nb2];
-            if (tc2_build_tap_matrix(taps_host, ntaps, h2, &p->tc2_sb_exp) == 0) {
-                e = cudaMalloc(&p->tc2_amat, nb2);
-                if (e == cudaSuccess) e = cudaMemcpy(p->tc2_amat, h2, nb2, cudaMemcpyHostToDevice);
-            }
-            delete[] h2;
-        }
+        delete[] h2;
     }
     if (e != cudaSuccess) {
         set_error("fir_plan_create: %s", cudaGetErrorString(e));
         cudaFree(p->taps_f32);
         cudaFree(p->taps_f64);
-        cudaFree(p->tc_bmat);
         cudaFree(p->tc2_amat);
         delete[] p->taps_host;
         delete p;
@@ -424,7 +402,6 @@ void b200dsp_fir_plan_destroy(b200dsp_fir_plan *plan)
     if (!plan) return;
     cudaFree(plan->taps_f32);
     cudaFree(plan->taps_f64);
-    cudaFree(plan->tc_bmat);
     cudaFree(plan->tc2_amat);
     for (int m = 0; m < 4; ++m)
         for (int q = 0; q < 5; ++q) cudaFree(plan->tcr_mat[m][q]);

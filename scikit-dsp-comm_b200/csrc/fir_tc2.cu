@@ -24,12 +24,11 @@
 // consumes it; tcgen05.commit recycles the stage.  Accumulators are double buffered per channel so the
 // epilogue (TMEM -> registers -> shuffle-combine hi/lo lanes -> coalesced complex64 stores) overlaps
 // the next channel's MMAs.
-#include "common.cuh"
-#include <cuda_fp16.h>
-#include <stdlib.h>
+#include "tc_common.cuh"
 
 namespace b200dsp {
 namespace tc2 {
+using namespace tcx;
 
 constexpr int BK = 64;                       // fp16 per 128-byte swizzle row = outputs per GEMM column block
 constexpr int NKB = 5;                       // k-blocks (256 taps + 64) / 64
@@ -42,11 +41,11 @@ template <int TN> struct Cfg {
     static constexpr int RAW_BYTES = TILE_IN * 8;
     static constexpr int STREAM_BYTES = ((ROWS * 128 + 1023) / 1024) * 1024;
     static constexpr int STAGE_BYTES = 4 * STREAM_BYTES; // >= RAW_BYTES: converted in place
-    static constexpr int NSTAGE = (TN == 64) ? 6 : 3;
+    static constexpr int NSTAGE = (TN == 64) ? 6 : (TN == 96 ? 4 : 3);
     static constexpr int SMEM_BAR_OFF = NSTAGE * STAGE_BYTES;
     static constexpr int SMEM_TOTAL = SMEM_BAR_OFF + 512 + 1024;
     static constexpr int ACC_BUF_COLS = TILE_N;          // one fp32 accumulator (128 lanes x TILE_N stream rows) per (tile, channel)
-    static constexpr int NACC = (TN == 64) ? 4 : 2;      // accumulator ring depth
+    static constexpr int NACC = (TN == 64) ? 4 : (TN == 96 ? 3 : 2);      // accumulator ring depth (160 + NACC*TN <= 512)
     static constexpr int F4_PER_TILE = TILE_IN / 2;
     static constexpr int F4_PER_THREAD = (F4_PER_TILE + 255) / 256;
     static constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -66,29 +65,6 @@ constexpr int N_CVT = N_CVT_WARPS * 32;      // 256
 constexpr int NTHREADS = (CVT_WARP0 + N_CVT_WARPS) * 32;    // 448
 constexpr int INV_RING = 16;
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int who) {
-    uint32_t done = 0;
-    for (uint32_t spin = 0; spin < (1u << 27); ++spin) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (done) return;
-    }
-    printf("b200dsp fir_tc2: mbarrier timeout (role %d, block %d)\n", who, (int)blockIdx.x);
-    __trap();
-}
 // bring-up instrumentation: cycles spent inside a wait, accumulated per call site
 template <bool DBG>
 __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, int who, long long &acc) {
@@ -100,66 +76,6 @@ __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, int w
         mbar_wait(bar, parity, who);
     }
 }
-// one elected lane of a converged warp (lets ptxas emit UTCHMMA / UBLKCP without a lane loop)
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem] (+)= A[tmem] * B[smem desc]
-__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
-          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-// K-major SWIZZLE_128B descriptor (see fir_tc.cu; the swizzle is a function of the absolute shared
-// address, so a start address that is not 1024-aligned needs base_offset = 0 -- measured on B200)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-
 struct Args {
     const float2 *x;
     const float2 *hist;
@@ -186,11 +102,6 @@ __device__ __forceinline__ bool tile_is_bulk(const Args &a, int64_t tile) {
     const int64_t g0 = tile * Cfg<TN>::TILE - HALO;
     return g0 >= 0 && g0 + Cfg<TN>::TILE_IN <= a.n && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0);
 }
-__device__ __forceinline__ uint32_t stream_off(int e) {
-    const int row = e >> 6, col = e & 63;
-    return (uint32_t)(row * 128 + ((((col >> 3) ^ (row & 7))) << 4) + ((col & 7) << 1));
-}
-
 template <int TN, bool DBG>
 __global__ void __launch_bounds__(NTHREADS, 1) fir_tc2_kernel(const Args a)
 {
@@ -382,7 +293,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc2_kernel(const Args a)
                     for (int pp = 0; pp < 2; ++pp) {
                         const int part = 1 - pp;
                         // descriptor of (stream, k-block 0, slice 0); only the 14-bit start field changes
-                        const uint64_t bd0 = make_desc(st + (2 * ch + part) * STREAM_BYTES);
+                        const uint64_t bd0 = make_desc_sw128(st + (2 * ch + part) * STREAM_BYTES);
 #pragma unroll
                         for (int jj = 0; jj < NKB; ++jj) {
                             constexpr int kOrder[NKB] = {0, 1, 4, 3, 2};
@@ -527,9 +438,11 @@ int launch_fir_tc2(const void *x, const void *hist, void *y, int64_t n, int32_t 
     if (const char *e = getenv("B200DSP_TC_DBG")) a.dbg = atoi(e);
     if (a.dbg) {
         if (tile_rows == 128) return launch_tc2_cfg<128, true>(a, n, sm_count, stream);
+        if (tile_rows == 96) return launch_tc2_cfg<96, true>(a, n, sm_count, stream);
         return launch_tc2_cfg<64, true>(a, n, sm_count, stream);
     }
     if (tile_rows == 128) return launch_tc2_cfg<128, false>(a, n, sm_count, stream);
+    if (tile_rows == 96) return launch_tc2_cfg<96, false>(a, n, sm_count, stream);
     return launch_tc2_cfg<64, false>(a, n, sm_count, stream);
 }
 
