@@ -135,6 +135,22 @@ struct ChunkReader {
     }
 };
 
+// ---- per-warp transposition buffers (fast path) ---------------------------------------------------
+// A warp owns 32 consecutive chunks.  Sub-block sb = the sb-th 128-byte piece of every chunk: 32 rows of
+// 128 B, each row contiguous in global memory.  cp.async moves it with fully coalesced 16-byte copies
+// (8 lanes per row, 4 rows per instruction) into a per-warp shared-memory buffer with a 144-byte row
+// pitch, so the per-lane 128-bit reads of "my row" are bank-conflict free.  Two buffers: the copy of
+// sub-block sb+1 overlaps the recurrence over sub-block sb.  (Lane-strided 128-bit global accesses cost
+// 32 L1 wavefronts per instruction; this path costs 4.)
+constexpr int SOS_ROW_UNITS = 9;                 // 8 x 16 B of data + 16 B pad per row
+constexpr int SOS_WBUF_BYTES = 2 * 32 * SOS_ROW_UNITS * 16;      // two stages per warp
+
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <typename S> struct VecOf {
     static constexpr int V = 16 / (int)sizeof(S);
     struct __align__(16) T { S v[16 / sizeof(S)]; };
@@ -162,28 +178,39 @@ __global__ void __launch_bounds__(SOS_NT) sos_pass1_kernel(const SosArgs<S, NSEC
 #pragma unroll
         for (int d = 0; d < D; ++d) z[c][d] = (C)0;
 
-    const bool fast = (a.L == 1) && (g0 + SOS_LC <= a.n_rate) && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0);
+    const int lane = tid & 31, warp = tid >> 5;
+    const int64_t wg0 = g0 - (int64_t)lane * SOS_LC;              // first sample of this warp's 32 chunks
+    const bool fast = (a.L == 1) && (wg0 + 32 * (int64_t)SOS_LC <= a.n_rate) && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0);
     if (fast) {
-        const Vec *px = reinterpret_cast<const Vec *>(a.x + g0);
-        constexpr int NB = SOS_LC / V, PF = 4;           // vectors per chunk, prefetch depth
-        Vec cur[PF];
+        Vec *wbuf = reinterpret_cast<Vec *>(smem_raw + sizeof(C) * ((size_t)SOS_LEVELS * D * D + (size_t)SOS_NT * D)) +
+                    (size_t)warp * (SOS_WBUF_BYTES / 16);
+        const Vec *wx = reinterpret_cast<const Vec *>(a.x + wg0);
+        constexpr int UPR = SOS_LC / V;                  // 16-byte units per chunk (row pitch in global memory)
+        constexpr int NSB = UPR / 8;                     // sub-blocks of 8 units (128 B) per chunk
+        auto issue = [&](int sb, int stage) {
 #pragma unroll
-        for (int k = 0; k < PF; ++k) cur[k] = px[k];
-#pragma unroll 1
-        for (int b = 0; b < NB; b += PF) {
-            Vec nxt[PF];
-            if (b + PF < NB) {
-#pragma unroll
-                for (int k = 0; k < PF; ++k) nxt[k] = px[b + PF + k];
+            for (int k = 0; k < 8; ++k) {
+                const int row = 4 * k + (lane >> 3), unit = lane & 7;
+                cp_async16(wbuf + (stage * 32 + row) * SOS_ROW_UNITS + unit, wx + (size_t)row * UPR + sb * 8 + unit);
             }
+            cp_async_commit();
+        };
+        issue(0, 0);
+#pragma unroll 1
+        for (int sb = 0; sb < NSB; ++sb) {
+            const int stage = sb & 1;
+            if (sb + 1 < NSB) { issue(sb + 1, stage ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+            __syncwarp();
+            const Vec *row = wbuf + (stage * 32 + lane) * SOS_ROW_UNITS;
 #pragma unroll
-            for (int k = 0; k < PF; ++k)
+            for (int u = 0; u < 8; ++u) {
+                const Vec vv = row[u];
 #pragma unroll
                 for (int e = 0; e < V; ++e)
 #pragma unroll
-                    for (int c = 0; c < NCH; ++c) sos_step<C, NSEC>(a.k, z[c], ch_get(cur[k].v[e], c));
-#pragma unroll
-            for (int k = 0; k < PF; ++k) cur[k] = nxt[k];
+                    for (int c = 0; c < NCH; ++c) sos_step<C, NSEC>(a.k, z[c], ch_get(vv.v[e], c));
+            }
+            __syncwarp();                                // buffer `stage` is free for sub-block sb+2
         }
     } else if (g0 < a.n_rate) {
         ChunkReader<S, NSEC> rd(a, g0);
@@ -253,33 +280,51 @@ __global__ void __launch_bounds__(SOS_NT) sos_pass2_kernel(const SosArgs<S, NSEC
 
     // corrected pass: true start state -> outputs
     const int64_t last = a.n_rate - 1 - g0;            // position of the stream's final sample in this chunk
-    const bool fast = (a.L == 1) && (a.M == 1) && (g0 + SOS_LC <= a.n_rate) && (a.zf == nullptr || last >= SOS_LC || last < 0) &&
+    const int lane = tid & 31, warp = tid >> 5;
+    const int64_t wg0 = g0 - (int64_t)lane * SOS_LC;
+    const int64_t wlast = a.n_rate - 1 - wg0;          // final sample relative to the warp's range
+    const bool fast = (a.L == 1) && (a.M == 1) && (wg0 + 32 * (int64_t)SOS_LC <= a.n_rate) &&
+                      (a.zf == nullptr || wlast >= 32 * (int64_t)SOS_LC || wlast < 0) &&
                       (((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.y)) & 15) == 0);
     if (fast) {
-        const Vec *px = reinterpret_cast<const Vec *>(a.x + g0);
-        Vec *py = reinterpret_cast<Vec *>(a.y + g0);
-        constexpr int NB = SOS_LC / V, PF = 4;
-        Vec cur[PF];
+        Vec *wbuf = reinterpret_cast<Vec *>(smem_raw + sizeof(C) * ((size_t)SOS_LEVELS * D * D + (size_t)SOS_NT * D)) +
+                    (size_t)warp * (SOS_WBUF_BYTES / 16);
+        const Vec *wx = reinterpret_cast<const Vec *>(a.x + wg0);
+        Vec *wy = reinterpret_cast<Vec *>(a.y + wg0);
+        constexpr int UPR = SOS_LC / V;
+        constexpr int NSB = UPR / 8;
+        auto issue = [&](int sb, int stage) {
 #pragma unroll
-        for (int k = 0; k < PF; ++k) cur[k] = px[k];
-#pragma unroll 1
-        for (int b = 0; b < NB; b += PF) {
-            Vec nxt[PF];
-            if (b + PF < NB) {
-#pragma unroll
-                for (int k = 0; k < PF; ++k) nxt[k] = px[b + PF + k];
+            for (int k = 0; k < 8; ++k) {
+                const int row = 4 * k + (lane >> 3), unit = lane & 7;
+                cp_async16(wbuf + (stage * 32 + row) * SOS_ROW_UNITS + unit, wx + (size_t)row * UPR + sb * 8 + unit);
             }
+            cp_async_commit();
+        };
+        issue(0, 0);
+#pragma unroll 1
+        for (int sb = 0; sb < NSB; ++sb) {
+            const int stage = sb & 1;
+            if (sb + 1 < NSB) { issue(sb + 1, stage ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+            __syncwarp();
+            Vec *row = wbuf + (stage * 32 + lane) * SOS_ROW_UNITS;
 #pragma unroll
-            for (int k = 0; k < PF; ++k) {
+            for (int u = 0; u < 8; ++u) {
+                const Vec vv = row[u];
                 Vec o;
 #pragma unroll
                 for (int e = 0; e < V; ++e)
 #pragma unroll
-                    for (int c = 0; c < NCH; ++c) ch_set(o.v[e], c, sos_step<C, NSEC>(a.k, z[c], ch_get(cur[k].v[e], c)));
-                py[b + k] = o;
+                    for (int c = 0; c < NCH; ++c) ch_set(o.v[e], c, sos_step<C, NSEC>(a.k, z[c], ch_get(vv.v[e], c)));
+                row[u] = o;                              // outputs replace the inputs in the warp buffer
             }
+            __syncwarp();
 #pragma unroll
-            for (int k = 0; k < PF; ++k) cur[k] = nxt[k];
+            for (int k = 0; k < 8; ++k) {                // coalesced write-back: 8 lanes per 128-byte row
+                const int r2 = 4 * k + (lane >> 3), unit = lane & 7;
+                wy[(size_t)r2 * UPR + sb * 8 + unit] = wbuf[(stage * 32 + r2) * SOS_ROW_UNITS + unit];
+            }
+            __syncwarp();
         }
     } else if (g0 < a.n_rate) {
         ChunkReader<S, NSEC> rd(a, g0);
@@ -457,7 +502,7 @@ static int run_group(const SosGroup &g, const S *x, S *y, int64_t n_in, int64_t 
 
     const size_t mats_bytes = sizeof(C) * (size_t)SOS_LEVELS * D * D;
     const size_t xch_bytes = sizeof(C) * (size_t)SOS_NT * D;
-    const size_t smem1 = mats_bytes + xch_bytes, smem3 = smem1;
+    const size_t smem1 = mats_bytes + xch_bytes + (size_t)(SOS_NT / 32) * SOS_WBUF_BYTES, smem3 = smem1;
     auto k1 = sos_pass1_kernel<S, NSEC>;
     auto k3 = sos_pass2_kernel<S, NSEC>;
     B200_CHECK_CUDA(allow_smem(k1, smem1));

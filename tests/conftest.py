@@ -72,3 +72,15 @@ def _build_oracle():
         oracle.build()
     except Exception as e:                       # pragma: no cover
         print("oracle C build failed, numpy/pure-Python oracle only:", e)
+
+
+@pytest.fixture(autouse=True)
+def _seed_everything():
+    """Deterministic inputs: every test starts from the same torch / numpy global seeds."""
+    np.random.seed(100)
+    try:
+        import torch
+        torch.manual_seed(100)
+    except Exception:
+        pass
+    yield

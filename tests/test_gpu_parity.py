@@ -213,7 +213,7 @@ def test_fir_up_dn_factors(mods, filters, factor):
 def test_fir_halo_equals_monolithic(mods, filters):
     """hist = overlap-save halo: chunked == monolithic.  Bit for bit on the CUDA-core kernels
     (fp64, and complex64 below the tensor-core length threshold); on the tensor-core complex64 path
-    the tile grid moves with the cut, so the fp32 accumulation order changes: equal to 1e-6*max|y|."""
+    the tile grid moves with the cut, so the fp32 accumulation order changes: equal to 2e-6*max|y| (each within 1e-6 of the oracle)."""
     from sk_dsp_comm_b200 import _engine
     b = filters["b256"]
     plan = _engine.FirPlan(b)
@@ -226,7 +226,7 @@ def test_fir_halo_equals_monolithic(mods, filters):
         def same(a, b_):
             if exact:
                 return torch.equal(a, b_)
-            return (a - b_).abs().max().item() <= 1e-6 * scale      # two fp32 results, each within ~4e-7
+            return (a - b_).abs().max().item() <= 2e-6 * scale      # two fp32 results, each within 1e-6 of the truth
 
         for cut in (255, 4096, 17777):
             y2 = _engine.fir_filter(plan, x[cut:].contiguous(), hist=x[cut - 255:cut].contiguous())
@@ -463,7 +463,7 @@ def test_cfg2_full_size_windows_and_properties(mods, filters):
     xs[d:] = x[:(1 << 22) - d]
     ys = _engine.fir_filter(plan, xs)
     # (the tensor-core tile grid is anchored at sample 0, so a shift changes the fp32 summation order)
-    assert (ys[d:] - y[:(1 << 22) - d]).abs().max().item() <= 1e-6 * y[:(1 << 22)].abs().max().item()
+    assert (ys[d:] - y[:(1 << 22) - d]).abs().max().item() <= 2e-6 * y[:(1 << 22)].abs().max().item()
     print("cfg2 worst window error / max|y| = %.3g" % worst)
 
 
@@ -520,17 +520,25 @@ def test_cfg4_sos6_2e28_float32(mods, filters):
 def test_host_pipeline_equals_device_path(mods, filters):
     """Chunked H2D|kernel|D2H pipeline (hostpipe.py) vs the monolithic device call.  The halo makes
     the chunked FILTER exact; on the tensor-core complex64 path the tile grid restarts at every chunk,
-    so fp32 summation order differs: equal to 4e-7*max|y| there, bit for bit on float64."""
+    so fp32 summation order differs (both within 1e-6*max|y| of the oracle); bit for bit on float64."""
     from sk_dsp_comm_b200 import _engine, hostpipe
     b = filters["b256"]
     plan = _engine.FirPlan(b)
+    torch.manual_seed(7)
     x = torch.randn((1 << 22) + 12345, dtype=torch.complex64).pin_memory()
     y_host = hostpipe.fir_filter_host(plan, x, chunk=1 << 20)
     y_dev = _engine.fir_filter(plan, x.cuda()).cpu()
     scale = y_dev.abs().max().item()
-    assert (y_host - y_dev).abs().max().item() <= 1e-6 * scale
+    # two fp32 evaluations with different tile grids: each is within 1e-6 of the float64 truth
+    assert (y_host - y_dev).abs().max().item() <= 2e-6 * scale
+    W = 1 << 15
+    for start in (0, (1 << 20) - 100, (3 << 20) + 5):          # windows straddling chunk boundaries
+        lo = max(start - 255, 0)
+        ref = oracle.fir_filter(b, x[lo:start + W].numpy().astype(np.complex128), backend="c")[start - lo:]
+        err, sc = _maxerr(y_host[start:start + W].numpy(), ref)
+        assert err <= FIR_TOL32 * sc, (start, err, sc)
     y_api = mods[0].multirate_FIR(b).filter(x)          # public API routes long host tensors here
-    assert (y_api - y_dev).abs().max().item() <= 1e-6 * scale
+    assert (y_api - y_dev).abs().max().item() <= 2e-6 * scale
     x64 = torch.randn((1 << 20) + 77, dtype=torch.float64).pin_memory()
     y_host = hostpipe.fir_filter_host(plan, x64, chunk=1 << 18)
     assert torch.equal(y_host, _engine.fir_filter(plan, x64.cuda()).cpu())
