@@ -274,8 +274,11 @@ static bool tcr_ready(b200dsp_fir_plan_impl *p, int mode, int P)
         int sb = 0;
         if (tcr_build(p->taps_host, p->ntaps, mode, P, hb, &sb) == 0) {
             void *d = nullptr;
+            // cudaMemcpy from pageable memory may return before the DMA has landed; the consumers run on
+            // non-blocking streams, so wait for the NULL stream explicitly
             if (cudaMalloc(&d, nb) == cudaSuccess &&
-                cudaMemcpy(d, hb, nb, cudaMemcpyHostToDevice) == cudaSuccess) {
+                cudaMemcpy(d, hb, nb, cudaMemcpyHostToDevice) == cudaSuccess &&
+                cudaStreamSynchronize(0) == cudaSuccess) {
                 p->tcr_mat[mode][P] = d;
                 p->tcr_sb[mode][P] = sb;
                 p->tcr_state[mode][P] = 1;
@@ -384,6 +387,9 @@ int b200dsp_fir_plan_create(const double *taps_host, int32_t ntaps, b200dsp_fir_
         }
         delete[] h2;
     }
+    // cudaMemcpy from pageable host memory may return before the DMA to the device has completed; kernels
+    // are launched on arbitrary (non-blocking) streams, so make the uploads visible to all of them now
+    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
     if (e != cudaSuccess) {
         set_error("fir_plan_create: %s", cudaGetErrorString(e));
         cudaFree(p->taps_f32);

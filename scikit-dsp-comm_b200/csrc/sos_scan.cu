@@ -668,6 +668,8 @@ int b200dsp_sos_plan_create(const double *sos_host, int32_t nsec, b200dsp_sos_pl
             if (e == cudaSuccess) e = cudaMalloc(&g.mats_f64, all.size() * sizeof(double));
             if (e == cudaSuccess) e = cudaMemcpy(g.mats_f32, allf.data(), allf.size() * sizeof(float), cudaMemcpyHostToDevice);
             if (e == cudaSuccess) e = cudaMemcpy(g.mats_f64, all.data(), all.size() * sizeof(double), cudaMemcpyHostToDevice);
+            // pageable-memory cudaMemcpy may return before the DMA completes; consumers use non-blocking streams
+            if (e == cudaSuccess) e = cudaStreamSynchronize(0);
         }
         p->groups.push_back(g);
         if (e != cudaSuccess) {

@@ -537,8 +537,12 @@ def test_host_pipeline_equals_device_path(mods, filters):
         ref = oracle.fir_filter(b, x[lo:start + W].numpy().astype(np.complex128), backend="c")[start - lo:]
         err, sc = _maxerr(y_host[start:start + W].numpy(), ref)
         assert err <= FIR_TOL32 * sc, (start, err, sc)
-    y_api = mods[0].multirate_FIR(b).filter(x)          # public API routes long host tensors here
-    assert (y_api - y_dev).abs().max().item() <= 2e-6 * scale
+    # public API routes long host tensors through the same pipeline; a brand-new filter object whose very
+    # first launch happens on a side stream must see its freshly uploaded tap matrices (regression: the
+    # plan upload is now synchronised before the plan is handed out)
+    for _ in range(3):
+        y_api = mods[0].multirate_FIR(b).filter(x)
+        assert (y_api - y_dev).abs().max().item() <= 2e-6 * scale
     x64 = torch.randn((1 << 20) + 77, dtype=torch.float64).pin_memory()
     y_host = hostpipe.fir_filter_host(plan, x64, chunk=1 << 18)
     assert torch.equal(y_host, _engine.fir_filter(plan, x64.cuda()).cpu())
