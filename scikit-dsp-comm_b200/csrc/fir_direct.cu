@@ -315,13 +315,13 @@ static int fir_dispatch(const b200dsp_fir_plan_impl *p, int dtype, const void *x
         // v == 10 forces it for any length, v == 9 forces the CUDA-core kernel.
         // Long complex64 streams: block-Toeplitz GEMM on the tensor cores (fir_tc2.cu, taps in TMEM).
         // Needs 16-byte aligned streams (bulk TMA in, vector stores out); otherwise the CUDA-core kernel.
-        //   v == 0 auto | 12 / 14 / 13 force the tensor-core kernel with 64 / 96 / 128-row tiles
-        //   | 9 force CUDA cores | 1..5 CUDA-core shapes
+        //   v == 0 auto (96-row tiles) | 12 / 15 / 14 / 13 force the tensor-core kernel with 64 / 80 / 96 / 128-row
+        //   tiles | 9 force CUDA cores | 1..5 CUDA-core shapes
         if (L == 1 && M == 1) {
             const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
-            if (p->tc2_amat != nullptr && (v == 12 || v == 13 || v == 14 || (v == 0 && n >= 32768 && aligned)))
+            if (p->tc2_amat != nullptr && (v == 12 || v == 13 || v == 14 || v == 15 || (v == 0 && n >= 32768 && aligned)))
                 return launch_fir_tc2(x, hist, y, n, hist_len, p->tc2_amat, p->tc2_sb_exp, p->ntaps,
-                                      v == 13 ? 128 : (v == 14 ? 96 : 64), p->sm_count, s);
+                                      v == 13 ? 128 : (v == 12 ? 64 : (v == 15 ? 80 : 96)), p->sm_count, s);
         }
         if (v == 1) return launch_fir_fit<float2, 16>(p, x, hist, y, n, n_m, L, M, hist_len, s, 256);
         if (v == 2) return launch_fir_fit<float2, 16>(p, x, hist, y, n, n_m, L, M, hist_len, s, 128);

@@ -41,11 +41,11 @@ template <int TN> struct Cfg {
     static constexpr int RAW_BYTES = TILE_IN * 8;
     static constexpr int STREAM_BYTES = ((ROWS * 128 + 1023) / 1024) * 1024;
     static constexpr int STAGE_BYTES = 4 * STREAM_BYTES; // >= RAW_BYTES: converted in place
-    static constexpr int NSTAGE = (TN == 64) ? 6 : (TN == 96 ? 4 : 3);
+    static constexpr int NSTAGE = (TN == 64) ? 6 : (TN == 80 ? 5 : (TN == 96 ? 4 : 3));
     static constexpr int SMEM_BAR_OFF = NSTAGE * STAGE_BYTES;
     static constexpr int SMEM_TOTAL = SMEM_BAR_OFF + 512 + 1024;
     static constexpr int ACC_BUF_COLS = TILE_N;          // one fp32 accumulator (128 lanes x TILE_N stream rows) per (tile, channel)
-    static constexpr int NACC = (TN == 64) ? 4 : (TN == 96 ? 3 : 2);      // accumulator ring depth (160 + NACC*TN <= 512)
+    static constexpr int NACC = (TN == 64) ? 4 : (TN == 80 ? 4 : (TN == 96 ? 3 : 2));   // accumulator ring depth (160 + NACC*TN <= 512)
     static constexpr int F4_PER_TILE = TILE_IN / 2;
     static constexpr int F4_PER_THREAD = (F4_PER_TILE + 255) / 256;
     static constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -439,10 +439,12 @@ int launch_fir_tc2(const void *x, const void *hist, void *y, int64_t n, int32_t 
     if (a.dbg) {
         if (tile_rows == 128) return launch_tc2_cfg<128, true>(a, n, sm_count, stream);
         if (tile_rows == 96) return launch_tc2_cfg<96, true>(a, n, sm_count, stream);
+        if (tile_rows == 80) return launch_tc2_cfg<80, true>(a, n, sm_count, stream);
         return launch_tc2_cfg<64, true>(a, n, sm_count, stream);
     }
     if (tile_rows == 128) return launch_tc2_cfg<128, false>(a, n, sm_count, stream);
     if (tile_rows == 96) return launch_tc2_cfg<96, false>(a, n, sm_count, stream);
+    if (tile_rows == 80) return launch_tc2_cfg<80, false>(a, n, sm_count, stream);
     return launch_tc2_cfg<64, false>(a, n, sm_count, stream);
 }
 

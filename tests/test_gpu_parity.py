@@ -253,12 +253,13 @@ def test_tensor_core_fir_tap_counts(mods, ntaps):
     n = 70001
     x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
     xt = torch.from_numpy(x).cuda()
-    mods[2].lib.b200dsp_set_fir_variant(12)
+    ref = oracle.fir_filter(b, x.astype(np.complex128), backend="c")
     try:
-        y = _engine.fir_filter(plan, xt).cpu().numpy()
-        ref = oracle.fir_filter(b, x.astype(np.complex128), backend="c")
-        err, scale = _maxerr(y, ref)
-        assert err <= FIR_TOL32 * scale, (ntaps, err, scale)
+        for variant in (12, 15, 14, 13):                 # 64 / 80 / 96 / 128-row tiles
+            mods[2].lib.b200dsp_set_fir_variant(variant)
+            y = _engine.fir_filter(plan, xt).cpu().numpy()
+            err, scale = _maxerr(y, ref)
+            assert err <= FIR_TOL32 * scale, (ntaps, variant, err, scale)
         if ntaps > 1:
             cut = 4096 * 3
             hist = xt[cut - (ntaps - 1):cut].contiguous()
