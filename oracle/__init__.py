@@ -62,6 +62,7 @@ def _clib():
         lib.oracle_fir_up_f64.argtypes = [P, I32, P, I64, I32, I32, P]
         lib.oracle_fir_dn_f64.argtypes = [P, I32, P, I64, I32, I32, P]
         lib.oracle_sosfilt_f64.argtypes = [P, I32, P, I64, I32, P, P, P]
+        lib.oracle_lfilter_ba_f64.argtypes = [P, P, I32, P, I64, P]
         lib.oracle_upsample_bytes.argtypes = [P, I64, I32, I32, P]
         lib.oracle_downsample_bytes.argtypes = [P, I64, I32, I32, I32, P]
         _lib = lib
@@ -245,6 +246,41 @@ def sos_up(sos, x, L):
 def sos_dn(sos, x, M):
     """``multirate_IIR.dn`` (multirate_helper.py:186-192)."""
     return downsample(sos_filter(sos, x), M)
+
+
+def lfilter_ba(b, a, x):
+    """``scipy.signal.lfilter(b, a, x)`` for real float64 data (direct form II transposed, zero state):
+    the arithmetic behind ``rate_change`` (multirate_helper.py:73-74,81-82) and ``interp24/deci24``."""
+    b = np.atleast_1d(np.asarray(b, dtype=np.float64))
+    a = np.atleast_1d(np.asarray(a, dtype=np.float64))
+    nc = max(len(b), len(a))
+    bp = np.zeros(nc)
+    ap = np.zeros(nc)
+    bp[:len(b)] = b
+    ap[:len(a)] = a
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.empty_like(x)
+    lib = _clib()
+    if lib is not None and nc <= 64:
+        lib.oracle_lfilter_ba_f64(_ptr(bp), _ptr(ap), nc, _ptr(x), x.shape[0], _ptr(y))
+        return y
+    z = np.zeros(nc)
+    for i in range(x.shape[0]):                      # small cases only
+        yi = bp[0] / ap[0] * x[i] + z[0]
+        for k in range(1, nc):
+            z[k - 1] = bp[k] / ap[0] * x[i] - ap[k] / ap[0] * yi + (z[k] if k + 1 < nc else 0.0)
+        y[i] = yi
+    return y
+
+
+def rate_change_up(b, a, x, M):
+    """``rate_change.up`` (multirate_helper.py:69-75)."""
+    return lfilter_ba(b, a, M * upsample(np.asarray(x), M))
+
+
+def rate_change_dn(b, a, x, M):
+    """``rate_change.dn`` (multirate_helper.py:77-83)."""
+    return downsample(lfilter_ba(b, a, x), M)
 
 
 def iir_order(sos):

@@ -154,3 +154,25 @@ void oracle_downsample_bytes(const void *x, int64_t n, int32_t M, int32_t p, int
     for (int64_t m = 0; m < nout; ++m)
         memcpy((char *)y + (size_t)m * esz, (const char *)x + (size_t)(m * M + p) * esz, esz);
 }
+
+/* scipy.signal.lfilter with a denominator: direct form II transposed,
+ *   y[n] = b0 x[n] + z0;  z_i = b_{i+1} x[n] - a_{i+1} y[n] + z_{i+1}   (a normalised by a0),
+ * zero initial state.  Called by rate_change.up/.dn (multirate_helper.py:73-74,81-82) and
+ * sigsys.interp24/deci24 (sigsys.py:2971-3027).  b and a are padded to the same length nc. */
+void oracle_lfilter_ba_f64(const double *b, const double *a, int32_t nc, const double *x, int64_t n, double *y)
+{
+    double z[64];
+    if (nc > 64 || nc < 1) return;
+    for (int i = 0; i < nc; ++i) z[i] = 0.0;
+    const double a0 = a[0];
+    for (int64_t i = 0; i < n; ++i) {
+        const double xi = x[i];
+        /* same operation order as scipy's _linear_filter inner loop */
+        const double yi = z[0] + (b[0] / a0) * xi;
+        for (int k = 1; k < nc; ++k) {
+            if (k + 1 < nc) z[k - 1] = (z[k] + (b[k] / a0) * xi) - (a[k] / a0) * yi;
+            else z[k - 1] = (b[k] / a0) * xi - (a[k] / a0) * yi;
+        }
+        y[i] = yi;
+    }
+}

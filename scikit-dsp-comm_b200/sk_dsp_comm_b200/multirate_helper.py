@@ -21,7 +21,9 @@ from logging import getLogger
 import numpy as np
 import torch
 
-from . import _engine
+import warnings
+
+from . import _design, _engine
 from ._io import Staged
 
 log = getLogger(__name__)
@@ -45,6 +47,83 @@ def _require_1d(x, what):
     if nd != 1:
         # the reference reaches sigsys.upsample/downsample, whose reshape rejects N-D input
         raise ValueError("%s expects a 1-D signal" % what)
+
+
+class _SosRunner(object):
+    """sosfilt / sosfilt(L*upsample) / downsample(sosfilt) on the GPU cascade for one sos array."""
+
+    def __init__(self, sos):
+        self._plan = _engine.SosPlan(np.asarray(sos, dtype=np.float64))
+
+    def filter(self, x):
+        st = Staged(x)
+        rows, shape = _rows(st.tensor)
+        outs = [_engine.sos_filter(self._plan, r) for r in rows]
+        y = outs[0] if shape is None else torch.stack(outs).reshape(shape)
+        return st.finish(y)
+
+    def up(self, x, L_change):
+        _require_1d(x, "up")
+        L = int(L_change - 1) + 1
+        if L < 1:
+            raise ValueError("negative dimensions are not allowed")
+        st = Staged(x)
+        y = _engine.sos_filter(self._plan, st.tensor.contiguous(), L=L)
+        if L != L_change:
+            y = y * (float(L_change) / L)
+        return st.finish(y)
+
+    def dn(self, x, M_change):
+        if not isinstance(M_change, int):
+            raise TypeError("M must be an int")
+        _require_1d(x, "dn")
+        st = Staged(x)
+        return st.finish(_engine.sos_filter(self._plan, st.tensor.contiguous(), M=M_change))
+
+
+class rate_change(object):
+    """
+    A simple class for encapsulating the upsample/filter and
+    filter/downsample operations used in modeling a comm
+    system. Objects of this class will hold the required filter
+    coefficients once an object is instantiated.
+
+    B200-native re-implementation of the reference class of the same name
+    (multirate_helper.py:45-83): same constructor, ``M``/``fc``/``N_forder``/``b``/``a`` attributes and
+    warning for an unknown ``ftype``.  The reference filters with the transfer-function form
+    ``lfilter(b, a, .)``; here the same Butterworth / Chebyshev-I design (``_design.py``) runs as a
+    second-order-section cascade on the GPU with the rate change fused in.
+    """
+
+    def __init__(self, M_change=12, fcutoff=0.9, N_filt_order=8, ftype='butter'):
+        """
+        Object constructor method
+        """
+        self.M = M_change            # Rate change factor M or L
+        self.fc = fcutoff * .5       # must be fs/(2*M), but scale by fcutoff
+        self.N_forder = N_filt_order
+        self._iir = None
+        if ftype.lower() == 'butter':
+            self.b, self.a, sos = _design.butter(self.N_forder, 2 / self.M * self.fc)
+        elif ftype.lower() == 'cheby1':
+            # Set the ripple to 0.05 dB
+            self.b, self.a, sos = _design.cheby1(self.N_forder, 0.05, 2 / self.M * self.fc)
+        else:
+            warnings.warn('ftype must be "butter" or "cheby1"')
+            return
+        self._iir = _SosRunner(sos)
+
+    def up(self, x):
+        """
+        Upsample and filter the signal
+        """
+        return self._iir.up(x, self.M)       # AttributeError for a bad ftype, like the reference (no self.b)
+
+    def dn(self, x):
+        """
+        Downsample and filter the signal
+        """
+        return self._iir.dn(x, self.M)
 
 
 class multirate_FIR(object):

@@ -18,6 +18,45 @@ from . import _engine
 from ._io import Staged
 
 
+_butter24 = {}
+
+
+def _butter10(M):
+    """10th-order Butterworth low-pass with cutoff 1/M as a GPU cascade (cached per M)."""
+    r = _butter24.get(M)
+    if r is None:
+        from . import _design
+        from .multirate_helper import _SosRunner
+        r = _SosRunner(_design.butter(10, 1.0 / M)[2])
+        _butter24[M] = r
+    return r
+
+
+def interp24(x):
+    """
+    Interpolate by L = 24 using Butterworth filters.
+
+    The interpolation is done using three stages. Upsample by
+    L = 2 and lowpass filter, upsample by 3 and lowpass filter, then
+    upsample by L = 4 and lowpass filter. In all cases the lowpass
+    filter is a 10th-order Butterworth lowpass (reference: sigsys.py:2945-2985);
+    every stage runs as one fused zero-stuff + biquad-cascade pass on the GPU.
+    """
+    y = _butter10(2).up(x, 2)
+    y = _butter10(3).up(y, 3)
+    return _butter10(4).up(y, 4)
+
+
+def deci24(x):
+    """
+    Decimate by L = 24 using Butterworth filters: lowpass + downsample by 2, 3 and 4
+    (reference: sigsys.py:2988-3028), each stage one fused cascade + decimation pass on the GPU.
+    """
+    y = _butter10(2).dn(x, 2)
+    y = _butter10(3).dn(y, 3)
+    return _butter10(4).dn(y, 4)
+
+
 def _is_arraylike_1d(x):
     if isinstance(x, torch.Tensor):
         if x.dim() != 1:

@@ -71,6 +71,13 @@ def rand(rng, n, dt):
 
 def main():
     filt = make_filters()
+    # "next" row: rate_change + interp24/deci24.  Coefficients come from the
+    # reference's own scipy calls; inputs of the two literal goldens are the reference's m-sequences.
+    import scipy.signal as _sig2
+    for M in (2, 3, 4):
+        bb, aa = _sig2.butter(10, 1.0 / M)
+        filt["butter10_%d_b" % M], filt["butter10_%d_a" % M] = bb, aa
+    filt["mseq2"], filt["mseq3"] = ss.m_seq(2), ss.m_seq(3)
     filt["iir_orders"] = np.array([mrh.multirate_IIR(filt[k]).N_forder
                                    for k in ("sos6", "sos_sharp_lpf", "sos_butter5", "sos_butter6")])
     np.savez_compressed(os.path.join(OUT, "filters.npz"), **filt)
@@ -130,6 +137,18 @@ def main():
         for M in (4, 12):
             x = rand(rng, 3000, "float64")
             add("sos_dn", fname, x, iir.dn(x, M), M=M)
+
+    # rate_change (multirate_helper.py:45-83)
+    for M, fcut, N, ftype in ((12, 0.9, 8, "butter"), (4, 0.8, 6, "cheby1"), (3, 0.9, 5, "butter")):
+        rc = mrh.rate_change(M, fcut, N, ftype)
+        x = rand(rng, 400, "float64")
+        add("rc_up", "", x, rc.up(x), M=M, fcut=fcut, N=N, ftype=ftype, b=rc.b.tolist(), a=rc.a.tolist())
+        x = rand(rng, 5000, "float32")
+        add("rc_dn", "", x, rc.dn(x), M=M, fcut=fcut, N=N, ftype=ftype, b=rc.b.tolist(), a=rc.a.tolist())
+    x = rand(rng, 100, "float64")
+    add("interp24", "", x, ss.interp24(x))
+    x = rand(rng, 6000, "float64")
+    add("deci24", "", x, ss.deci24(x))
 
     # upsample / downsample (sigsys.py:3031-3083)
     for dt in ("float32", "float64", "complex64", "complex128", "int16"):

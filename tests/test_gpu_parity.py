@@ -58,6 +58,14 @@ def _run(mods, c, filters, x):
         return mrh.multirate_IIR(filters[c["filt"]]).up(x, c["L"])
     if k == "sos_dn":
         return mrh.multirate_IIR(filters[c["filt"]]).dn(x, c["M"])
+    if k == "rc_up":
+        return mrh.rate_change(c["M"], c["fcut"], c["N"], c["ftype"]).up(x)
+    if k == "rc_dn":
+        return mrh.rate_change(c["M"], c["fcut"], c["N"], c["ftype"]).dn(x)
+    if k == "interp24":
+        return ss.interp24(x)
+    if k == "deci24":
+        return ss.deci24(x)
     if k == "upsample":
         return ss.upsample(x, c["L"])
     if k == "downsample":
@@ -80,6 +88,8 @@ def test_reference_fixtures_numpy_in_numpy_out(mods, filters):
         else:
             err, scale = _maxerr(y, ref)
             tol = FIR_TOL64 if c["kind"].startswith("fir") else IIR_TOL64
+            if c["kind"] in ("rc_up", "rc_dn", "interp24", "deci24"):
+                tol = 1e-7       # cascade vs the reference's transfer-function form (bar: rtol 1e-4)
             assert err <= tol * scale, (c["name"], c["kind"], c.get("filt"), err, scale)
         n += 1
     assert n > 150
@@ -134,6 +144,32 @@ def test_ten_band_biquad_cascade_known_answer(mods, filters):
               -0.76767407, -1.95402381, -1.0580526, 0.9111369]
     y = mods[0].multirate_IIR(filters["sos_tenband"]).filter(filters["tenband_w"])
     npt.assert_almost_equal(y, y_test)
+
+
+def test_interp24_deci24_known_answers(mods, filters):
+    # /root/reference/tests/test_sigsys.py:617-653: literal goldens through upsample + Butterworth chains
+    from test_oracle_golden import INTERP24_GOLDEN, DECI24_GOLDEN
+    ss = mods[1]
+    npt.assert_almost_equal(ss.interp24(filters["mseq2"]), INTERP24_GOLDEN)
+    npt.assert_almost_equal(ss.deci24(ss.interp24(filters["mseq3"])), DECI24_GOLDEN)
+
+
+def test_rate_change_surface(mods):
+    """rate_change keeps the reference's constructor / attributes / warning (multirate_helper.py:45-83)."""
+    import inspect
+    import warnings as _w
+    mrh = mods[0]
+    assert str(inspect.signature(mrh.rate_change.__init__)) == "(self, M_change=12, fcutoff=0.9, N_filt_order=8, ftype='butter')"
+    rc = mrh.rate_change()
+    assert rc.M == 12 and rc.fc == 0.45 and rc.N_forder == 8 and len(rc.b) == 9 and len(rc.a) == 9
+    with _w.catch_warnings(record=True) as rec:
+        _w.simplefilter("always")
+        mrh.rate_change(ftype="bessel")
+    assert any("butter" in str(r.message) for r in rec)
+    x = torch.randn(100000, dtype=torch.float32, device="cuda")
+    y = rc.up(x)
+    assert y.is_cuda and y.dtype == torch.float32 and y.numel() == 12 * x.numel()
+    assert rc.dn(x).numel() == x.numel() // 12
 
 
 def test_upsample_downsample_reference_tests(mods):
