@@ -237,7 +237,7 @@ def run_gpu(args):
     achieved = ALGO_BYTES_PER_SAMPLE * n / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": dram_traffic_per_launch(),
-                "peak_source": peak_src, "kernel": "fir_tc_kernel (tcgen05 block-Toeplitz, fp16 hi/lo split)" if args.variant in (0, 10) else "fir_poly_kernel<float2,float,R,NT>",
+                "peak_source": peak_src, "kernel": "fir_tc2_kernel<96> (tcgen05 block-Toeplitz GEMM, taps in TMEM, fp16 hi/lo split)" if args.variant == 0 else "variant %d" % args.variant,
                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SAMPLE * n,
                 "kernel_ms": k_ms, "kernel_ms_min": min(per_step)}
 
