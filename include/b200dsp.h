@@ -93,18 +93,20 @@ int b200dsp_sos_plan_create(const double *sos_host, int32_t nsec, b200dsp_sos_pl
 void b200dsp_sos_plan_destroy(b200dsp_sos_plan *plan);
 int32_t b200dsp_sos_plan_nsec(const b200dsp_sos_plan *plan);
 
-/* Bytes of device scratch b200dsp_sos_filter needs for an n-sample call of this dtype / L. */
-size_t b200dsp_sos_workspace_bytes(const b200dsp_sos_plan *plan, int dtype, int64_t n, int32_t L);
+/* Bytes of device scratch b200dsp_sos_filter needs for an n-sample call of this dtype / L / M. */
+size_t b200dsp_sos_workspace_bytes(const b200dsp_sos_plan *plan, int dtype, int64_t n, int32_t L, int32_t M);
 
 /* Biquad cascade in direct-form-II-transposed arithmetic, run as a parallel-prefix
  * recurrence (chunked zero-state pass -> scan of chunk carries -> corrected pass).
  *   L == 1, M == 1 : y = sosfilt(sos, x)                         multirate_helper.py:169-174
  *   L  > 1         : y = sosfilt(sos, L*upsample(x,L)), n*L outputs          (:177-183)
  *   M  > 1         : y = downsample(sosfilt(sos,x), M), floor(n/M) outputs   (:186-192)
+ *                    (long calls stage the full-rate stream once in the workspace; an IIR runs at the
+ *                    full rate in any case)
  * zi: initial state, 2*nsec values per channel laid out [section][2][channel] in the
  *     dtype's real scalar type (scipy's zi layout), or NULL = zeros (the reference never
  *     passes zi).  zf: final state written in the same layout, or NULL.
- * ws / ws_bytes: scratch of at least b200dsp_sos_workspace_bytes(plan, dtype, n, L). */
+ * ws / ws_bytes: scratch of at least b200dsp_sos_workspace_bytes(plan, dtype, n, L, M). */
 int b200dsp_sos_filter(const b200dsp_sos_plan *plan, int dtype, const void *x, void *y, int64_t n,
                        int32_t L, int32_t M, const void *zi, void *zf, void *ws, size_t ws_bytes,
                        void *stream);

@@ -10,9 +10,9 @@ namespace b200dsp {
 // side) so stores are full-width and perfectly coalesced; one integer division per vector, the
 // element index then advances incrementally.  Reads touch each x element once per vector that
 // overlaps its row (L1/L2 hits).
-template <typename E, typename IDX>
+template <typename E, typename IDX, bool GAIN = false>
 __global__ void __launch_bounds__(256) upsample_vec_kernel(const E *__restrict__ x, E *__restrict__ y,
-                                                          int64_t n_out, int32_t L)
+                                                          int64_t n_out, int32_t L, typename Sample<E>::C gain = 1)
 {
     constexpr int VEC = 16 / (int)sizeof(E);
     struct __align__(16) Pack { E v[VEC]; };
@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(256) upsample_vec_kernel(const E *__restrict__
         Pack pk;
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
-            pk.v[e] = (r == 0) ? x[q] : zero_of(E());
+            pk.v[e] = (r == 0) ? (GAIN ? scale_of(x[q], gain) : x[q]) : zero_of(E());
             if (++r == L) { r = 0; ++q; }
         }
         reinterpret_cast<Pack *>(y)[vi] = pk;
@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(256) upsample_vec_kernel(const E *__restrict__
     const int64_t t = n_vec * VEC + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n_out) {
         int64_t q = t / L;
-        y[t] = (q * L == t) ? x[q] : zero_of(E());
+        y[t] = (q * L == t) ? (GAIN ? scale_of(x[q], gain) : x[q]) : zero_of(E());
     }
 }
 
@@ -105,6 +105,42 @@ static int dn_launch(const void *x, void *y, int64_t n_out, int32_t M, int32_t p
     downsample_kernel<E><<<grid_for(n_out, sm_count_cached()), 256, 0, st>>>((const E *)x, (E *)y, n_out, M, p);
     B200_CHECK_LAUNCH("downsample_kernel");
     return B200DSP_OK;
+}
+
+// ---- internal helpers for the SOS cascade's rate-change staging (sos_scan.cu) ----
+template <typename E>
+static int up_gain_launch(const void *x, void *y, int64_t n, int32_t L, double gain, cudaStream_t st)
+{
+    using C = typename Sample<E>::C;
+    const int64_t n_out = n * L;
+    constexpr int VEC = 16 / (int)sizeof(E);
+    unsigned g = grid_for((n_out + VEC - 1) / VEC, sm_count_cached());
+    upsample_vec_kernel<E, int64_t, true><<<g, 256, 0, st>>>((const E *)x, (E *)y, n_out, L, (C)gain);
+    B200_CHECK_LAUNCH("upsample_vec_kernel(gain)");
+    return B200DSP_OK;
+}
+
+// y (16-byte aligned) = gain * zero-stuffed x
+int resample_up_scaled(int dtype, const void *x, void *y, int64_t n, int32_t L, double gain, cudaStream_t st)
+{
+    switch (dtype) {
+    case B200DSP_F32: return up_gain_launch<float>(x, y, n, L, gain, st);
+    case B200DSP_F64: return up_gain_launch<double>(x, y, n, L, gain, st);
+    case B200DSP_C64: return up_gain_launch<float2>(x, y, n, L, gain, st);
+    case B200DSP_C128: return up_gain_launch<double2>(x, y, n, L, gain, st);
+    }
+    return B200DSP_E_DTYPE;
+}
+
+int resample_dn(int dtype, const void *x, void *y, int64_t n_out, int32_t M, cudaStream_t st)
+{
+    switch (dtype) {
+    case B200DSP_F32: return dn_launch<float>(x, y, n_out, M, 0, st);
+    case B200DSP_F64: return dn_launch<double>(x, y, n_out, M, 0, st);
+    case B200DSP_C64: return dn_launch<float2>(x, y, n_out, M, 0, st);
+    case B200DSP_C128: return dn_launch<double2>(x, y, n_out, M, 0, st);
+    }
+    return B200DSP_E_DTYPE;
 }
 
 }  // namespace b200dsp

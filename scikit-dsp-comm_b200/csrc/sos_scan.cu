@@ -571,6 +571,20 @@ static size_t sos_scan_area_bytes(int dtype, int64_t n_rate)
     return 2 * a + (size_t)n_tiles * per_tile * SOS_NT + 256;
 }
 
+// resample.cu
+int resample_up_scaled(int dtype, const void *x, void *y, int64_t n, int32_t L, double gain, cudaStream_t st);
+int resample_dn(int dtype, const void *x, void *y, int64_t n_out, int32_t M, cudaStream_t st);
+
+constexpr int64_t SOS_STAGE_MIN = 1 << 16;     // full-rate staging pays off above this many filter-rate samples
+
+static bool sos_needs_tmp(size_t ngroups, int64_t n_rate, int32_t L, int32_t M)
+{
+    return ngroups > 1 || ((L > 1 || M > 1) && n_rate >= SOS_STAGE_MIN);
+}
+
+// Long rate-changing calls run the cascade on the vectorised full-rate path: the (L x gain) zero-stuffed
+// input or the undecimated output is staged once in the workspace by the streaming index-map kernels
+// (an IIR has to run at the full rate anyway); short calls use the fused element-wise path.
 template <typename S>
 static int sos_run(const b200dsp_sos_plan_impl *p, const S *x, S *y, int64_t n, int32_t L, int32_t M,
                    const void *zi, void *zf, unsigned char *ws, int dtype, cudaStream_t st)
@@ -581,20 +595,37 @@ static int sos_run(const b200dsp_sos_plan_impl *p, const S *x, S *y, int64_t n, 
     const int64_t n_out = n_rate / M;
     const size_t ng = p->groups.size();
     S *tmp = nullptr;
-    if (ng > 1) tmp = reinterpret_cast<S *>(ws + ((sos_scan_area_bytes(dtype, n_rate) + 255) & ~(size_t)255));
+    if (sos_needs_tmp(ng, n_rate, L, M))
+        tmp = reinterpret_cast<S *>(ws + ((sos_scan_area_bytes(dtype, n_rate) + 255) & ~(size_t)255));
+    const bool stage = (L > 1 || M > 1) && n_rate >= SOS_STAGE_MIN;
+    const S *src0 = x;
+    int64_t n_in0 = n;
+    int32_t L0 = L, M_last = M;
+    if (stage) {
+        if (L > 1) {
+            int rc = resample_up_scaled(dtype, x, tmp, n, L, (double)L, st);
+            if (rc != B200DSP_OK) return rc;
+            src0 = tmp;
+            n_in0 = n_rate;
+            L0 = 1;
+        }
+        M_last = 1;
+    }
     size_t sec0 = 0;
     for (size_t gi = 0; gi < ng; ++gi) {
         const SosGroup &g = p->groups[gi];
         const bool first = gi == 0, last = gi + 1 == ng;
-        const S *src = first ? x : tmp;
-        S *dst = last ? y : tmp;
+        const S *src = first ? src0 : tmp;
+        S *dst = (last && !(stage && M > 1)) ? y : tmp;
         const C *zig = zi ? static_cast<const C *>(zi) + sec0 * 2 * NCH : nullptr;
         C *zfg = zf ? static_cast<C *>(zf) + sec0 * 2 * NCH : nullptr;
-        int rc = run_group_nsec<S>(g, src, dst, first ? n : n_rate, n_rate, last ? n_out : n_rate,
-                                   first ? L : 1, last ? M : 1, zig, zfg, ws, st);
+        int rc = run_group_nsec<S>(g, src, dst, first ? n_in0 : n_rate, n_rate,
+                                   (last && M_last > 1) ? n_out : n_rate,
+                                   first ? L0 : 1, last ? M_last : 1, zig, zfg, ws, st);
         if (rc != B200DSP_OK) return rc;
         sec0 += g.nsec_real;
     }
+    if (stage && M > 1) return resample_dn(dtype, tmp, y, n_out, M, st);
     return B200DSP_OK;
 }
 
@@ -694,12 +725,12 @@ void b200dsp_sos_plan_destroy(b200dsp_sos_plan *plan)
 
 int32_t b200dsp_sos_plan_nsec(const b200dsp_sos_plan *plan) { return plan ? plan->nsec : 0; }
 
-size_t b200dsp_sos_workspace_bytes(const b200dsp_sos_plan *plan, int dtype, int64_t n, int32_t L)
+size_t b200dsp_sos_workspace_bytes(const b200dsp_sos_plan *plan, int dtype, int64_t n, int32_t L, int32_t M)
 {
-    if (!plan || n < 0 || L < 1 || dtype_size(dtype) == 0) return 0;
+    if (!plan || n < 0 || L < 1 || M < 1 || dtype_size(dtype) == 0) return 0;
     const int64_t n_rate = n * L;
     size_t b = (sos_scan_area_bytes(dtype, n_rate) + 255) & ~(size_t)255;
-    if (plan->groups.size() > 1) b += (size_t)n_rate * dtype_size(dtype) + 256;
+    if (sos_needs_tmp(plan->groups.size(), n_rate, L, M)) b += (size_t)n_rate * dtype_size(dtype) + 256;
     return b;
 }
 
@@ -716,9 +747,9 @@ int b200dsp_sos_filter(const b200dsp_sos_plan *plan, int dtype, const void *x, v
         return B200DSP_E_DTYPE;
     }
     if (n == 0) return B200DSP_OK;
-    if (!ws || ws_bytes < b200dsp_sos_workspace_bytes(plan, dtype, n, L)) {
+    if (!ws || ws_bytes < b200dsp_sos_workspace_bytes(plan, dtype, n, L, M)) {
         set_error("sos_filter: workspace too small (%zu < %zu)", ws_bytes,
-                  b200dsp_sos_workspace_bytes(plan, dtype, n, L));
+                  b200dsp_sos_workspace_bytes(plan, dtype, n, L, M));
         return B200DSP_E_WORKSPACE;
     }
     unsigned char *w = static_cast<unsigned char *>(ws);

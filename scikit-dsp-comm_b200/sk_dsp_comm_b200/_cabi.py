@@ -58,7 +58,7 @@ def _load():
     lib.b200dsp_sos_plan_destroy.restype = None
     lib.b200dsp_sos_plan_nsec.argtypes = [P]
     lib.b200dsp_sos_plan_nsec.restype = I32
-    lib.b200dsp_sos_workspace_bytes.argtypes = [P, I, I64, I32]
+    lib.b200dsp_sos_workspace_bytes.argtypes = [P, I, I64, I32, I32]
     lib.b200dsp_sos_workspace_bytes.restype = SZ
     lib.b200dsp_sos_filter.argtypes = [P, I, P, P, I64, I32, I32, P, P, P, SZ, P]
     lib.b200dsp_upsample.argtypes = [I, P, P, I64, I32, P]

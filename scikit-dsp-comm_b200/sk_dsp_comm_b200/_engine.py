@@ -158,7 +158,7 @@ def sos_filter(plan: SosPlan, x: torch.Tensor, L: int = 1, M: int = 1, zi=None, 
     if n > 0:
         with torch.cuda.device(dev):
             h = plan.handle(dev)
-            nbytes = int(lib.b200dsp_sos_workspace_bytes(h, code, n, L))
+            nbytes = int(lib.b200dsp_sos_workspace_bytes(h, code, n, L, M))
             ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
             check(lib.b200dsp_sos_filter(h, code, x.data_ptr(), y.data_ptr(), n, L, M,
                                          zi.data_ptr() if zi is not None else None,

@@ -411,6 +411,37 @@ def test_sos_section_counts(mods, nsec):
     assert err <= IIR_TOL64 * scale, (nsec, "up", err, scale)
 
 
+@pytest.mark.parametrize("dt", ["float32", "float64", "complex64"])
+def test_sos_up_dn_long_streams(mods, filters, dt):
+    """multirate_IIR.up/.dn on streams long enough for the staged full-rate path (>= 2^16 filter-rate
+    samples), incl. a 10-section cascade (two launch groups) and the final state zf."""
+    from sk_dsp_comm_b200 import _engine
+    rng = np.random.default_rng(5)
+    n = 100003
+    x = rng.standard_normal(n)
+    if "complex" in dt:
+        x = x + 1j * rng.standard_normal(n)
+    x = x.astype(dt)
+    tol = IIR_TOL32 if dt in ("float32", "complex64") else IIR_TOL64
+    # the ten-band equaliser (10 sections = two launch groups) has poles at radius 0.9988: in float32 the
+    # recursion itself is only good to ~1e-4, so that cascade is checked in float64 only
+    for fname in (("sos6", "sos_tenband") if dt == "float64" else ("sos6", "sos_butter5")):
+        sos = filters[fname]
+        iir = mods[0].multirate_IIR(sos)
+        xt = torch.from_numpy(x).cuda()
+        for F in (4, 12):
+            err, scale = _maxerr(iir.dn(xt, F).cpu().numpy(), oracle.sos_dn(sos, x, F))
+            assert err <= tol * scale, (fname, dt, "dn", F, err, scale)
+            xs = x[:30011]
+            err, scale = _maxerr(iir.up(torch.from_numpy(xs).cuda(), F).cpu().numpy(), oracle.sos_up(sos, xs, F))
+            assert err <= tol * scale, (fname, dt, "up", F, err, scale)
+    if dt == "float64":
+        plan = _engine.SosPlan(filters["sos6"])
+        _, zf = _engine.sos_filter(plan, torch.from_numpy(x).cuda(), M=4, return_zf=True)
+        _, zf_ref = oracle.sos_filter(filters["sos6"], x, return_zf=True)
+        npt.assert_allclose(zf.cpu().numpy(), zf_ref, rtol=0, atol=1e-9 * max(1.0, np.abs(zf_ref).max()))
+
+
 def test_sos_state_carry(mods, filters):
     """zi/zf chaining reproduces the monolithic run (the multi-GPU / streaming hook)."""
     from sk_dsp_comm_b200 import _engine

@@ -33,6 +33,10 @@ report("downsample4 f32 2^26 (s + s/M)", x.numel(), 5 * x.numel(), timeit(lambda
 x = torch.randn(2 ** 28, dtype=torch.float32, device="cuda")
 report("fir256 f32 2^28", x.numel(), 8 * x.numel(), timeit(lambda: _engine.fir_filter(fir256, x), reps=5))
 report("cfg4 sos6 f32 2^28", x.numel(), 8 * x.numel(), timeit(lambda: _engine.sos_filter(sos6, x), reps=5))
+x26 = x[:2 ** 26]
+report("sos6 dn4 f32 2^26 (multirate_IIR.dn)", x26.numel(), 5 * x26.numel(), timeit(lambda: _engine.sos_filter(sos6, x26, M=4), reps=5))
+x24 = x[:2 ** 24]
+report("sos6 up4 f32 2^24 (multirate_IIR.up)", x24.numel(), 20 * x24.numel(), timeit(lambda: _engine.sos_filter(sos6, x24, L=4), reps=5))
 del x
 x = torch.randn(2 ** 26, dtype=torch.float64, device="cuda")
 report("sos6 f64 2^26", x.numel(), 16 * x.numel(), timeit(lambda: _engine.sos_filter(sos6, x), reps=5))
