@@ -56,13 +56,15 @@ constexpr int HALO = (NKB - 1) * BK;         // 256
 constexpr int A_COLS = KTOT / 2;             // 160 TMEM columns of packed fp16 pairs
 constexpr int ACC_COL0 = A_COLS;             // accumulators start here
 
-constexpr int N_EPI_WARPS = 4;               // warps 0-3 (TMEM lanes 32w..32w+31)
+constexpr int N_EPI_WARPS = 8;               // warps 0-3 and 14-17: a warp reads TMEM lanes 32*(warp%4)..+31; the
+                                             // two groups split the accumulator columns between them
+constexpr int EPI2_WARP0 = 14;
 constexpr int MMA_WARP = 4;
 constexpr int PROD_WARP = 5;
 constexpr int CVT_WARP0 = 6;
 constexpr int N_CVT_WARPS = 8;
 constexpr int N_CVT = N_CVT_WARPS * 32;      // 256
-constexpr int NTHREADS = (CVT_WARP0 + N_CVT_WARPS) * 32;    // 448
+constexpr int NTHREADS = (EPI2_WARP0 + 4) * 32;              // 576
 constexpr int INV_RING = 16;
 
 // bring-up instrumentation: cycles spent inside a wait, accumulated per call site
@@ -149,7 +151,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc2_kernel(const Args a)
     const uint32_t tmem_base = *tmem_slot;
 
     // ---- tap matrix -> TMEM (A operand, stays for the whole kernel) ----
-    if (warp < N_EPI_WARPS) {
+    if (warp < 4) {
         const int row = warp * 32 + lane;                                  // TMEM lane == matrix row
         const uint4 *src = a.amat + (size_t)row * (KTOT * 2 / 16);         // 40 uint4 per row
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc2_kernel(const Args a)
         }
         if (DBG && (a.dbg & 8) && blockIdx.x == 1 && lane == 0)
             printf("tc2 producer: tiles %d total %lld wait_a_empty %lld\n", it, clock64() - t_start, w0);
-    } else if (warp >= CVT_WARP0) {
+    } else if (warp >= CVT_WARP0 && warp < CVT_WARP0 + N_CVT_WARPS) {
         // =============================== converters ===============================
         const int ct = tid - CVT_WARP0 * 32;
         int it = 0;
@@ -317,45 +319,64 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc2_kernel(const Args a)
         if (DBG && (a.dbg & 8) && blockIdx.x == 1 && lane == 0)
             printf("tc2 mma: tiles %d total %lld wait_a_full %lld wait_d_empty %lld\n", it, clock64() - t_start, w0, w1);
     } else {
-        // =============================== epilogue (warps 0-3) ===============================
-        // Lane l < 16 holds row b_hi[c], lane l+16 row b_lo[c] (c = 16*warp + l): y = (D[l] + D[l+16]) * inv.
-        // Hi-row lanes finish even stream rows, lo-row lanes the odd ones, so all 32 lanes store.
+        // =============================== epilogue (warps 0-3 and 14-17) ===============================
+        // Lane l < 16 holds row b_hi[c], lane l+16 row b_lo[c] (c = 16*q + l, q = warp % 4 = TMEM lane quarter):
+        // y = (D[l] + D[l+16]) * inv.  Hi-row lanes finish even stream rows, lo-row lanes the odd ones, so all
+        // 32 lanes store.  The two warp groups take the lower / upper half of the accumulator columns.
         int it = 0;
         uint32_t unit = 0;
-        const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+        const int q4 = warp & 3, grp = (warp < 4) ? 0 : 1;
+        const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
         const bool lo_row = lane >= 16;
-        const int c = warp * 16 + (lane & 15);
+        const int c = q4 * 16 + (lane & 15);
+        constexpr int NCHUNK = TILE_N / 16;
+        const int ch_lo = grp == 0 ? 0 : (NCHUNK + 1) / 2, ch_hi = grp == 0 ? (NCHUNK + 1) / 2 : NCHUNK;
         long long w0 = 0, t_start = DBG ? clock64() : 0;
+        constexpr int CPG = (NCHUNK + 1) / 2;               // column chunks per warp group
         for (int64_t tile = first; tile < a.n_tiles; tile += step, ++it, unit += 2) {
             const uint32_t b_re = unit % NACC, b_im = (unit + 1) % NACC;
-            mbar_wait_t<DBG>(D_FULL(b_re), (unit / NACC) & 1u, 4, w0);
-            mbar_wait_t<DBG>(D_FULL(b_im), ((unit + 1) / NACC) & 1u, 4, w0);
-            tc_fence_after();
-            const float inv = tile_inv[it % INV_RING];
             const uint32_t d_re = tmem_base + lane_sel + ACC_COL0 + b_re * ACC_BUF_COLS;
             const uint32_t d_im = tmem_base + lane_sel + ACC_COL0 + b_im * ACC_BUF_COLS;
             const int64_t g_c = tile * TILE + c + (lo_row ? BK : 0);
-#pragma unroll 1
-            for (int c0 = 0; c0 < TILE_N; c0 += 16) {
-                uint32_t dr[16], di[16];
-                tmem_ld16(d_re + c0, dr);
-                tmem_ld16(d_im + c0, di);
-                tmem_ld_wait();
-                if (c0 + 16 == TILE_N) {                     // both accumulators are in registers: release them
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) { mbar_arrive(D_EMPTY(b_re)); mbar_arrive(D_EMPTY(b_im)); }
-                }
+            // real-part accumulator: pull this warp's columns into registers and hand the TMEM slot back
+            // immediately -- the MMA warp can refill it while the imaginary part is still being computed
+            mbar_wait_t<DBG>(D_FULL(b_re), (unit / NACC) & 1u, 4, w0);
+            tc_fence_after();
+            uint32_t dr[CPG][16];
 #pragma unroll
-                for (int q = 0; q < 16; q += 2) {
-                    const float sr = __uint_as_float(lo_row ? dr[q] : dr[q + 1]);
-                    const float si = __uint_as_float(lo_row ? di[q] : di[q + 1]);
-                    const float rr = __shfl_xor_sync(0xffffffffu, sr, 16);
-                    const float ri = __shfl_xor_sync(0xffffffffu, si, 16);
-                    const float vr = (rr + __uint_as_float(lo_row ? dr[q + 1] : dr[q])) * inv;
-                    const float vi = (ri + __uint_as_float(lo_row ? di[q + 1] : di[q])) * inv;
-                    const int64_t g = g_c + (int64_t)(c0 + q) * BK;
-                    if ((!DBG || !(a.dbg & 4)) && g < a.n) a.y[g] = make_float2(vr, vi);
+            for (int k = 0; k < CPG; ++k)
+                if (ch_lo + k < ch_hi) tmem_ld16(d_re + (ch_lo + k) * 16, dr[k]);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(D_EMPTY(b_re));
+            mbar_wait_t<DBG>(D_FULL(b_im), ((unit + 1) / NACC) & 1u, 4, w0);
+            tc_fence_after();
+            const float inv = tile_inv[it % INV_RING];
+#pragma unroll
+            for (int k = 0; k < CPG; ++k) {
+                const int ck = ch_lo + k;
+                if (ck < ch_hi) {
+                    const int c0 = ck * 16;
+                    uint32_t di[16];
+                    tmem_ld16(d_im + c0, di);
+                    tmem_ld_wait();
+                    if (ck + 1 == ch_hi) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(D_EMPTY(b_im));
+                    }
+#pragma unroll
+                    for (int q = 0; q < 16; q += 2) {
+                        const float sr = __uint_as_float(lo_row ? dr[k][q] : dr[k][q + 1]);
+                        const float si = __uint_as_float(lo_row ? di[q] : di[q + 1]);
+                        const float rr = __shfl_xor_sync(0xffffffffu, sr, 16);
+                        const float ri = __shfl_xor_sync(0xffffffffu, si, 16);
+                        const float vr = (rr + __uint_as_float(lo_row ? dr[k][q + 1] : dr[k][q])) * inv;
+                        const float vi = (ri + __uint_as_float(lo_row ? di[q + 1] : di[q])) * inv;
+                        const int64_t g = g_c + (int64_t)(c0 + q) * BK;
+                        if ((!DBG || !(a.dbg & 4)) && g < a.n) a.y[g] = make_float2(vr, vi);
+                    }
                 }
             }
         }
