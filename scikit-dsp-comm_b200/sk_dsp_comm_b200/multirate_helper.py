@@ -81,6 +81,22 @@ class _SosRunner(object):
         return st.finish(_engine.sos_filter(self._plan, st.tensor.contiguous(), M=M_change))
 
 
+def _fir_final_state(b, tail, zi, N):
+    """lfilter's final delay values of an FIR after N samples: ``tail`` = the last min(N, K-1)
+    inputs, ``zi`` the K-1 initial values (what is left of them after N shifts is added)."""
+    K = len(b)
+    m = len(tail)
+    zf = np.zeros(K - 1, dtype=zi.dtype)
+    rev = tail[::-1]                                  # rev[j] = x[N-1-j]
+    for i in range(K - 1):
+        nj = min(K - 1 - i, m)
+        if nj:
+            zf[i] = np.dot(b[i + 1:i + 1 + nj], rev[:nj])
+    if N < K - 1:
+        zf[:K - 1 - N] += zi[N:]
+    return zf
+
+
 class rate_change(object):
     """
     A simple class for encapsulating the upsample/filter and
@@ -153,10 +169,16 @@ class multirate_FIR(object):
         self._plan = _engine.FirPlan(barr.astype(np.float64))
 
     # -- reference: y = signal.lfilter(self.b,[1],x)  (multirate_helper.py:104-109)
-    def filter(self, x):
+    def filter(self, x, zi=None):
         """
         Filter the signal
+
+        ``zi`` (extension): the ``len(b)-1`` filter delay values of
+        ``scipy.signal.lfilter(b, [1], x, zi=zi)``; when given, ``(y, zf)`` is returned and ``zf``
+        fed back as the next call's ``zi`` continues the stream exactly where this block ended.
         """
+        if zi is not None:
+            return self._filter_stateful(x, zi)
         if isinstance(x, torch.Tensor) and not x.is_cuda and x.dim() == 1 \
                 and x.numel() >= _HOST_PIPE_MIN and x.dtype in _engine.DTYPE_CODE:
             from . import hostpipe
@@ -166,6 +188,35 @@ class multirate_FIR(object):
         outs = [_engine.fir_filter(self._plan, r) if r.numel() else r.clone() for r in rows]
         y = outs[0] if shape is None else torch.stack(outs).reshape(shape)
         return st.finish(y)
+
+    def _filter_stateful(self, x, zi):
+        """lfilter's transposed-direct-form state for an FIR: with zero input the state simply
+        drains, ``y[n] += zi[n]`` for ``n < K-1``, and the final state is the tail of the
+        convolution that has not left the filter yet,
+        ``zf[i] = sum_{j} b[i+1+j] x[N-1-j] + zi[i+N]``  (scipy _signaltools.lfilter / _linear_filter).
+        The block itself runs in the FIR kernel; only the K-1 state values are handled here."""
+        _require_1d(x, "filter(zi=...)")
+        K = self._plan.ntaps
+        st = Staged(x)
+        t = st.tensor.contiguous()
+        N = t.numel()
+        z = np.asarray(zi.detach().cpu() if isinstance(zi, torch.Tensor) else zi).reshape(-1)
+        if z.size != K - 1:
+            raise ValueError("Unexpected shape for zi: expected (%d,), found %s." % (K - 1, tuple(np.shape(zi))))
+        cplx = t.is_complex() or np.iscomplexobj(z)
+        z = z.astype(np.complex128 if cplx else np.float64)
+        if cplx and not t.is_complex():
+            t = t.to(torch.complex64 if t.dtype == torch.float32 else torch.complex128)
+        y = _engine.fir_filter(self._plan, t) if N else t.clone()
+        m = min(K - 1, N)
+        if m:
+            y[:m] += torch.from_numpy(z[:m]).to(device=y.device, dtype=y.dtype)
+        # final state from the last min(N, K-1) inputs (2 KB for 256 taps) in float64 on the host
+        zf = _fir_final_state(self._plan.taps, t[N - m:].cpu().numpy().astype(z.dtype), z, N)
+        if st.kind == "numpy":
+            return st.finish(y), zf
+        zf_t = torch.from_numpy(zf)
+        return st.finish(y), (zf_t.to(t.device) if st.kind == "cuda" else zf_t)
 
     # -- reference: y = L*upsample(x,L); y = lfilter(b,[1],y)  (multirate_helper.py:112-118)
     def up(self, x, L_change=12):
@@ -250,11 +301,39 @@ class multirate_IIR(object):
         return self._plan
 
     # -- reference: y = signal.sosfilt(self.sos,x)  (multirate_helper.py:169-174)
-    def filter(self, x):
+    def filter(self, x, zi=None):
         """
         Filter the signal using second-order sections
+
+        ``zi`` (extension): ``(n_sections, 2)`` section delay values in
+        ``scipy.signal.sosfilt``'s layout; when given, ``(y, zf)`` is returned.  The parallel-prefix
+        kernel carries the same transposed-direct-form-II state, so chunked calls chained through
+        ``zf`` reproduce the monolithic result.
         """
         plan = self._get_plan()
+        if zi is not None:
+            _require_1d(x, "filter(zi=...)")
+            st = Staged(x)
+            t = st.tensor.contiguous()
+            z = zi if isinstance(zi, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(zi)))
+            if tuple(z.shape) != (plan.nsec, 2):
+                raise ValueError("Invalid zi shape. With axis=-1, an input with shape %s, and an sos array "
+                                 "with %d sections, zi must have shape (%d, 2), got %s."
+                                 % (tuple(t.shape), plan.nsec, plan.nsec, tuple(z.shape)))
+            if z.is_complex():
+                if not t.is_complex():
+                    t = t.to(torch.complex64 if t.dtype == torch.float32 else torch.complex128)
+                z = torch.view_as_real(z.to(torch.complex128).contiguous())          # (nsec, 2, re/im)
+            elif t.is_complex():
+                z = torch.stack([z.to(torch.float64), torch.zeros_like(z, dtype=torch.float64)], dim=-1)
+            y, zf = _engine.sos_filter(plan, t, zi=z, return_zf=True)
+            if t.is_complex():
+                zf = torch.view_as_complex(zf.to(torch.float64).contiguous())
+            else:
+                zf = zf.to(torch.float64)
+            if st.kind == "numpy":
+                return st.finish(y), zf.cpu().numpy()
+            return st.finish(y), (zf if st.kind == "cuda" else zf.cpu())
         st = Staged(x)
         rows, shape = _rows(st.tensor)
         outs = [_engine.sos_filter(plan, r) for r in rows]

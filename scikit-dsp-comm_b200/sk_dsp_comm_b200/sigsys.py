@@ -172,3 +172,147 @@ def downsample(x, M, p=0):
     elif narrow:
         out = out.to(x.dtype)
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Pulse-shaped line codes (reference: sigsys.py:1847-2202).  The waveform is
+# one launch of the fused zero-stuff + FIR kernel (``_pulse.shape_symbols``); bits come from the
+# legacy ``np.random`` generator in the reference's order so seeded runs reproduce its output.
+
+from . import _pulse                                             # noqa: E402
+from ._pulse import rc_imp, sqrt_rc_imp, m_seq, pn_gen           # noqa: E402,F401
+
+
+def _nrz_pulse(pulse, ns, alpha, m):
+    b = _pulse.pulse_taps(pulse, ns, alpha, m)
+    if b is None:
+        raise ValueError('pulse type must be rec, rc, or src')
+    return b
+
+
+def nrz_bits(n_bits, ns, pulse='rect', alpha=0.25, m=6):
+    """
+    Generate non-return-to-zero (NRZ) data bits with pulse shaping.
+
+    A baseband digital data signal using +/-1 amplitude signal values and including pulse
+    shaping ('rect', 'rc' or 'src'; ``2*m*ns + 1`` taps for the latter two).  Returns the
+    waveform, ``b / ns`` and the 0/1 bits (reference: sigsys.py:2099-2150).
+    """
+    data = np.random.randint(0, 2, n_bits)
+    b = _nrz_pulse(pulse, ns, alpha, m)
+    x = _pulse.shape_symbols(2.0 * data - 1, b, ns)
+    return x, b / float(ns), data
+
+
+def nrz_bits2(data, Ns, pulse='rect', alpha=0.25, M=6):
+    """
+    NRZ with user supplied 0/1 ``data`` (reference: sigsys.py:2153-2202); returns the waveform
+    and ``b / Ns``.
+    """
+    b = _nrz_pulse(pulse, Ns, alpha, M)
+    d = np.asarray(data)
+    x = _pulse.shape_symbols(2 * d.reshape(len(d)) - 1, b, Ns)
+    return x, b / float(Ns)
+
+
+def bpsk_tx(N_bits, Ns, ach_fc=2.0, ach_lvl_dB=-100, pulse='rect', alpha=0.25, M=6):
+    """
+    BPSK transmitter with adjacent channel interference: the wanted NRZ stream plus two more at
+    ``+/- ach_fc/Ns`` cycles/sample and ``ach_lvl_dB`` (reference: sigsys.py:2053-2096; only
+    'rect' and 'src' pulses are accepted there).
+    """
+    if pulse not in ('rect', 'src'):
+        raise ValueError('Pulse shape must be \'rect\' or \'src\'')
+    x0, b, data0 = nrz_bits(N_bits, Ns, pulse, alpha, M)
+    x1p, b, _ = nrz_bits(N_bits, Ns, pulse, alpha, M)
+    x1m, b, _ = nrz_bits(N_bits, Ns, pulse, alpha, M)
+    n = np.arange(len(x0))
+    x1p = x1p * np.exp(1j * 2 * np.pi * ach_fc / float(Ns) * n)
+    x1m = x1m * np.exp(-1j * 2 * np.pi * ach_fc / float(Ns) * n)
+    ach_lvl = 10 ** (ach_lvl_dB / 20.)
+    return x0 + ach_lvl * (x1p + x1m), b, data0
+
+
+# ---------------------------------------------------------------------------------------------
+# Block FIR filtering (SURVEY.md 8f rank 3; reference: sigsys.py:482-598).  The reference walks
+# the signal in FFT frames of N samples (overlap-save / overlap-add) to obtain exactly the linear
+# convolution truncated to len(x); the FIR kernel already is an overlap-save over shared-memory
+# tiles, so the filtered output is one launch.  ``mode=1`` rebuilds the per-frame diagnostic rows
+# (circular convolution of each frame for overlap-save, the zero-padded frame's linear
+# convolution for overlap-add) with one launch per frame.
+
+def _block_filter_args(x, h, N):
+    h = np.asarray(h)
+    if h.ndim != 1 or h.size == 0:
+        raise ValueError("h must be a non-empty 1-D sequence of taps")
+    if h.dtype.kind == "c":
+        raise NotImplementedError("complex FIR taps are not supported by the B200 engine")
+    P = len(h)
+    L = int(N) - P + 1
+    if L < 1:
+        raise ValueError("FFT size N must be at least len(h)")
+    x = np.asarray(x)
+    if x.ndim != 1:
+        raise ValueError("x must be 1-D")
+    # the reference keeps np.real(ifft(.)): with real taps that is the filtered real part of x
+    x = np.ascontiguousarray(x.real, dtype=np.float64)
+    return x, h.astype(np.float64), P, L
+
+
+def _run_fir(plan, seg, hist=None):
+    st = Staged(seg)
+    hd = None if hist is None else torch.from_numpy(np.ascontiguousarray(hist)).to(st.tensor.device)
+    return st.finish(_engine.fir_filter(plan, st.tensor, hist=hd))
+
+
+def os_filter(x, h, N, mode=0):
+    """
+    Overlap and save transform domain FIR filtering.
+
+    Returns ``y`` (``len(x)`` samples of ``h * x``) and, for ``mode == 1``, the diagnostic matrix
+    whose row ``k`` holds frame ``k``'s circular-convolution output placed at its position in the
+    stream (reference: sigsys.py:482-540).
+    """
+    x, h, P, L = _block_filter_args(x, h, N)
+    N = int(N)
+    plan = _engine.FirPlan(h)
+    n_x = len(x)
+    y = _run_fir(plan, x) if n_x else x.copy()
+    if mode != 1:
+        return y
+    Nx = n_x + P - 1
+    Nframe = int(np.ceil(Nx / float(L)))
+    xp = np.hstack((np.zeros(P - 1), x, np.zeros(Nframe * L - Nx + (N - L))))
+    y_mat = np.zeros((Nframe, int(Nframe * N)))
+    for k in range(Nframe):
+        xk = xp[k * L:k * L + N]
+        if len(xk) < N:
+            xk = np.hstack((xk, np.zeros(N - len(xk))))
+        # circular convolution of the frame == linear filter whose history is the frame's own tail
+        hist = xk[N - (P - 1):] if P > 1 else None
+        y_mat[k, k * L:k * L + N] = _run_fir(plan, xk, hist)
+    return y, y_mat[:, P - 1:Nx]
+
+
+def oa_filter(x, h, N, mode=0):
+    """
+    Overlap and add transform domain FIR filtering.
+
+    Returns ``y`` (``len(x)`` samples of ``h * x``) and, for ``mode == 1``, the diagnostic matrix
+    whose row ``k`` holds the ``N``-sample response of frame ``k`` (``L = N - len(h) + 1`` inputs)
+    at its position in the stream (reference: sigsys.py:543-598).
+    """
+    x, h, P, L = _block_filter_args(x, h, N)
+    N = int(N)
+    plan = _engine.FirPlan(h)
+    Nx = len(x)
+    y = _run_fir(plan, x) if Nx else x.copy()
+    if mode != 1:
+        return y
+    Nframe = int(np.ceil(Nx / float(L)))
+    xp = np.hstack((x, np.zeros(Nframe * L - Nx)))
+    y_mat = np.zeros((Nframe, Nframe * N))
+    for k in range(Nframe):
+        xk = np.hstack((xp[k * L:(k + 1) * L], np.zeros(N - L)))
+        y_mat[k, k * L:k * L + N] = _run_fir(plan, xk)
+    return y, y_mat[:, 0:Nx]

@@ -1,0 +1,153 @@
+"""Streaming state (zi/zf) and block filtering against fixtures from
+scipy's lfilter/sosfilt ``zi`` argument and the reference's os_filter/oa_filter
+(tests/golden/make_stream_golden.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+S = np.load(os.path.join(GOLDEN, "stream_cases.npz"))
+F = np.load(os.path.join(GOLDEN, "filters.npz"))
+TABLE = json.loads(str(S["table"]))
+FIRZ = [c for c in TABLE if c["kind"] == "firz"]
+SOSZ = [c for c in TABLE if c["kind"] == "sosz"]
+BLK = [c for c in TABLE if c["kind"] == "blk"]
+
+FIR_TOL, IIR_TOL = 1e-11, 1e-9
+
+
+def _rel(got, want):
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    return float(np.abs(got - want).max()) / max(float(np.abs(want).max()), 1e-300) if want.size else 0.0
+
+
+# ------------------------------------------------------------------------------ CPU: host logic
+
+@pytest.mark.parametrize("c", FIRZ, ids=[c["key"] for c in FIRZ])
+def test_fir_final_state_formula(c):
+    """zf of lfilter's transposed FIR from the last K-1 inputs + what is left of zi."""
+    from sk_dsp_comm_b200.multirate_helper import _fir_final_state
+    k = c["key"]
+    b, x, zi = F[c["filt"]], S[k + "_x"], S[k + "_zi"]
+    cplx = np.iscomplexobj(x) or np.iscomplexobj(zi)
+    dt = np.complex128 if cplx else np.float64
+    m = min(len(b) - 1, len(x))
+    zf = _fir_final_state(b, x[len(x) - m:].astype(dt), zi.astype(dt), len(x))
+    assert _rel(zf, S[k + "_zf"]) <= 1e-13 if zf.size else True
+
+
+# ------------------------------------------------------------------------------ GPU
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("c", FIRZ, ids=[c["key"] for c in FIRZ])
+def test_gpu_fir_zi_zf(c):
+    import sk_dsp_comm_b200.multirate_helper as mrh
+    k = c["key"]
+    fir = mrh.multirate_FIR(F[c["filt"]])
+    y, zf = fir.filter(S[k + "_x"], zi=S[k + "_zi"])
+    assert y.dtype == S[k + "_y"].dtype and zf.dtype == S[k + "_zf"].dtype
+    assert _rel(y, S[k + "_y"]) <= FIR_TOL
+    if zf.size:
+        assert _rel(zf, S[k + "_zf"]) <= FIR_TOL
+
+
+@pytest.mark.gpu
+def test_gpu_fir_zi_promotes_and_validates():
+    import sk_dsp_comm_b200.multirate_helper as mrh
+    fir = mrh.multirate_FIR(F["b7"])
+    y, zf = fir.filter(S["firz_promote_x"], zi=S["firz_promote_zi"])
+    assert y.dtype == np.complex128
+    assert _rel(y, S["firz_promote_y"]) <= FIR_TOL and _rel(zf, S["firz_promote_zf"]) <= FIR_TOL
+    with pytest.raises(ValueError, match="Unexpected shape for zi"):
+        fir.filter(np.zeros(10), zi=np.zeros(5))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["float64", "complex64"])
+def test_gpu_fir_chunked_stream_equals_monolithic(dtype):
+    """Chaining zf -> zi over ragged chunks (one shorter than the filter) reproduces one call."""
+    import torch
+    import sk_dsp_comm_b200.multirate_helper as mrh
+    rng = np.random.default_rng(4)
+    n = 100000
+    x = rng.standard_normal(n)
+    if dtype == "complex64":
+        x = (x + 1j * rng.standard_normal(n)).astype(np.complex64)
+    fir = mrh.multirate_FIR(F["b256"])
+    xt = torch.from_numpy(x).cuda()
+    whole = fir.filter(xt)
+    z = np.zeros(255)
+    parts = []
+    for lo, hi in ((0, 40000), (40000, 40100), (40100, 40101), (40101, n)):
+        y, z = fir.filter(xt[lo:hi], zi=z)
+        assert y.is_cuda and z.is_cuda and y.dtype == xt.dtype
+        parts.append(y)
+    got = torch.cat(parts)
+    tol = FIR_TOL if dtype == "float64" else 1e-6
+    assert float((got - whole).abs().max()) <= tol * float(whole.abs().max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("c", SOSZ, ids=[c["key"] for c in SOSZ])
+def test_gpu_sos_zi_zf(c):
+    import sk_dsp_comm_b200.multirate_helper as mrh
+    k = c["key"]
+    iir = mrh.multirate_IIR(F[c["filt"]])
+    y, zf = iir.filter(S[k + "_x"], zi=S[k + "_zi"])
+    assert y.dtype == S[k + "_y"].dtype and zf.shape == S[k + "_zf"].shape and zf.dtype == S[k + "_zf"].dtype
+    assert _rel(y, S[k + "_y"]) <= IIR_TOL
+    assert _rel(zf, S[k + "_zf"]) <= IIR_TOL
+
+
+@pytest.mark.gpu
+def test_gpu_sos_chunked_stream_equals_monolithic():
+    import torch
+    import sk_dsp_comm_b200.multirate_helper as mrh
+    x = torch.from_numpy(np.random.default_rng(6).standard_normal(300000)).cuda()
+    iir = mrh.multirate_IIR(F["sos6"])
+    whole = iir.filter(x)
+    z = np.zeros((6, 2))
+    parts = []
+    for lo, hi in ((0, 70001), (70001, 70002), (70002, 200000), (200000, 300000)):
+        y, z = iir.filter(x[lo:hi], zi=z)
+        parts.append(y)
+    got = torch.cat(parts)
+    assert float((got - whole).abs().max()) <= IIR_TOL * float(whole.abs().max())
+    with pytest.raises(ValueError, match="Invalid zi shape"):
+        iir.filter(x[:10], zi=np.zeros((5, 2)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("c", BLK, ids=[c["name"] for c in BLK])
+def test_gpu_block_filters(c):
+    import sk_dsp_comm_b200.sigsys as ss
+    name, N = c["name"], c["N"]
+    x, h = S["blk_%s_x" % name], S["blk_%s_h" % name]
+    for fn in ("os_filter", "oa_filter"):
+        want = S["blk_%s_%s_y" % (name, fn)]
+        y = getattr(ss, fn)(x, h, N)
+        assert y.dtype == np.float64 and _rel(y, want) <= 1e-10          # the reference's FFT path carries ~1e-13
+        key = "blk_%s_%s_ymat" % (name, fn)
+        if key in S.files and S[key].shape[0] <= 64:
+            y1, ymat = getattr(ss, fn)(x, h, N, 1)
+            assert np.array_equal(y1, y)
+            assert ymat.shape == S[key].shape
+            assert np.abs(ymat - S[key]).max() <= 1e-10 * max(np.abs(S[key]).max(), 1.0)
+
+
+@pytest.mark.gpu
+def test_gpu_block_filter_literal_golden():
+    """tests/test_sigsys.py:688-706."""
+    import sk_dsp_comm_b200.sigsys as ss
+    y_test = [1., 1.95105652, 2.76007351, 3.34785876, 3.65687576, 3.65687576, 3.34785876, 2.76007351,
+              1.95105652, 1., -1., -2.90211303, -4.52014702, -5.69571753, -6.31375151,
+              -6.31375151, -5.69571753, -4.52014702, -2.90211303, -1.]
+    x = np.cos(2 * np.pi * 0.05 * np.arange(0, 20))
+    np.testing.assert_almost_equal(ss.os_filter(x, np.ones(10), 2 ** 10), y_test)
+    np.testing.assert_almost_equal(ss.oa_filter(x, np.ones(10), 2 ** 10), y_test)
+    with pytest.raises(ValueError):
+        ss.os_filter(x, np.ones(10), 8)
