@@ -157,6 +157,101 @@ __global__ void __launch_bounds__(NT) fir_poly_kernel(const FirArgs<S, C> a)
 }
 
 // ------------------------------------------------------------------------------------------
+// Short-phase interpolation: up(L) with few taps per phase (pulse shaping: 97-tap SRC at 8
+// samples/symbol is 13 taps per phase).  fir_poly_kernel pads every phase to a multiple of its R
+// and stages L*TILE outputs in shared memory, both of which hurt when Q = ceil(K/L) is small; here
+// a thread owns ONE input position m and produces all L outputs y[L m .. L m + L-1] in chunks of
+// RP phases held in registers: per tap index q one shared-memory sample (lane-consecutive, conflict
+// free) and one broadcast vector of RP taps feed RP FMAs.  Each thread's outputs are contiguous, so
+// they leave as 16-byte vector stores straight from registers (a warp covers 32*L consecutive
+// elements); the kernel is used when L*sizeof(sample) is a multiple of 16 so that every m starts
+// on a 16-byte boundary.  Accumulation order (q ascending, gain folded into the taps) is the same
+// as fir_poly_kernel's.
+template <typename S> struct VecStore;
+template <> struct VecStore<float> {
+    static constexpr int EPV = 4;
+    static __device__ __forceinline__ void st(float *p, const float *a) {
+        *reinterpret_cast<float4 *>(p) = make_float4(a[0], a[1], a[2], a[3]);
+    }
+};
+template <> struct VecStore<float2> {
+    static constexpr int EPV = 2;
+    static __device__ __forceinline__ void st(float2 *p, const float2 *a) {
+        *reinterpret_cast<float4 *>(p) = make_float4(a[0].x, a[0].y, a[1].x, a[1].y);
+    }
+};
+template <> struct VecStore<double> {
+    static constexpr int EPV = 2;
+    static __device__ __forceinline__ void st(double *p, const double *a) {
+        *reinterpret_cast<double2 *>(p) = make_double2(a[0], a[1]);
+    }
+};
+template <> struct VecStore<double2> {
+    static constexpr int EPV = 1;
+    static __device__ __forceinline__ void st(double2 *p, const double2 *a) { *p = a[0]; }
+};
+
+template <typename S, typename C, int RP, int NT, bool PK>
+__global__ void __launch_bounds__(NT) fir_up_short_kernel(const FirArgs<S, C> a)
+{
+    constexpr int TV = 16 / (int)sizeof(C);          // taps per 16-byte broadcast load
+    constexpr int EPV = VecStore<S>::EPV;            // output elements per 16-byte store
+    static_assert(RP % TV == 0 && RP % EPV == 0, "phase chunk must be whole vectors");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int Q = a.kq;                              // taps per phase (not padded)
+    const int L = a.L;
+    const int LP = ((L + RP - 1) / RP) * RP;         // phases padded to whole chunks
+    C *hs = reinterpret_cast<C *>(smem_raw);         // hs[q*LP + r] = L * b[L q + r]
+    const size_t taps_bytes = ((size_t)Q * LP * sizeof(C) + 15) & ~(size_t)15;
+    S *xs = reinterpret_cast<S *>(smem_raw + taps_bytes);   // xs[i] = x[m_t - (Q-1) + i]
+    const int64_t m_t = (int64_t)blockIdx.x * NT;
+    {
+        const C gain = (C)L;
+        for (int v = tid; v < Q * LP; v += NT) {
+            const int q = v / LP, r = v - q * LP;
+            const int64_t k = (int64_t)q * L + r;
+            hs[v] = (r < L && k < a.ntaps) ? gain * a.taps[k] : (C)0;
+        }
+    }
+    for (int v = tid; v < NT + Q - 1; v += NT) {
+        const int64_t g = m_t - (Q - 1) + v;
+        S val = zero_of(S());
+        if (g >= 0) {
+            if (g < a.n_in) val = a.x[g];
+        } else if (a.hist != nullptr) {
+            const int64_t hidx = (int64_t)a.hist_len + g;
+            if (hidx >= 0) val = a.hist[hidx];
+        }
+        xs[v] = val;
+    }
+    __syncthreads();
+    const int64_t m = m_t + tid;
+    if (m >= a.n_m) return;
+    S *yo = a.y + m * L;
+    const S *xp = xs + tid + (Q - 1);                // x[m]; x[m-q] = xp[-q]
+    for (int r0 = 0; r0 < L; r0 += RP) {
+        S acc[RP];
+#pragma unroll
+        for (int r = 0; r < RP; ++r) acc[r] = zero_of(S());
+        const C *hp = hs + r0;
+        for (int q = 0; q < Q; ++q) {
+            const S xv = xp[-q];
+#pragma unroll
+            for (int r4 = 0; r4 < RP; r4 += TV) {
+                const TapVec<C> tv = *reinterpret_cast<const TapVec<C> *>(hp + r4);
+#pragma unroll
+                for (int u = 0; u < TV; ++u) MacOp<S, PK>::run(acc[r4 + u], tv.v[u], xv);
+            }
+            hp += LP;
+        }
+#pragma unroll
+        for (int r = 0; r < RP; r += EPV)
+            if (r0 + r + EPV <= L) VecStore<S>::st(yo + r0 + r, acc + r);     // L % EPV == 0: no ragged tail
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 struct b200dsp_fir_plan_impl {
     int32_t ntaps;
     float *taps_f32;
@@ -264,6 +359,45 @@ static int launch_fir_fit(const b200dsp_fir_plan_impl *p, const void *x, const v
     return rc;
 }
 
+// up(L) through fir_up_short_kernel when the filter has few taps per phase and every output row starts on a
+// 16-byte boundary; B200DSP_E_UNSUPPORTED = not eligible (caller falls back to fir_poly_kernel).
+template <typename S, int RP, bool PK = false>
+static int launch_fir_up_short(const b200dsp_fir_plan_impl *p, const void *x, const void *hist, void *y,
+                               int64_t n, int32_t L, int32_t hist_len, cudaStream_t stream)
+{
+    using C = typename Sample<S>::C;
+    constexpr int NT = 256;
+    constexpr int QMAX = 32;
+    const int Q = (p->ntaps + L - 1) / L;
+    if (L < 2 || Q > QMAX || ((size_t)L * sizeof(S)) % 16 != 0 || (reinterpret_cast<uintptr_t>(y) & 15) != 0)
+        return B200DSP_E_UNSUPPORTED;
+    const int LP = ((L + RP - 1) / RP) * RP;
+    const size_t taps_bytes = ((size_t)Q * LP * sizeof(C) + 15) & ~(size_t)15;
+    const size_t smem = taps_bytes + (size_t)(NT + Q - 1) * sizeof(S);
+    if (smem > 96 * 1024) return B200DSP_E_UNSUPPORTED;
+    const int64_t tiles = (n + NT - 1) / NT;
+    if (tiles > 2147483647LL) return B200DSP_E_UNSUPPORTED;
+    FirArgs<S, C> a;
+    a.x = static_cast<const S *>(x);
+    a.hist = static_cast<const S *>(hist);
+    a.y = static_cast<S *>(y);
+    a.taps = sizeof(C) == 4 ? reinterpret_cast<const C *>(p->taps_f32)
+                            : reinterpret_cast<const C *>(p->taps_f64);
+    a.n_in = n;
+    a.n_m = n;
+    a.ntaps = p->ntaps;
+    a.kq = Q;
+    a.hist_len = hist_len;
+    a.L = L;
+    a.M = 1;
+    a.lg = 1;
+    auto kern = fir_up_short_kernel<S, C, RP, NT, PK>;
+    B200_CHECK_CUDA(allow_smem(kern, smem));
+    kern<<<(unsigned)tiles, NT, smem, stream>>>(a);
+    B200_CHECK_LAUNCH("fir_up_short_kernel");
+    return B200DSP_OK;
+}
+
 // Lazily build (and cache in the plan) the TMEM tap matrices of one float32 tensor-core mode.
 static bool tcr_ready(b200dsp_fir_plan_impl *p, int mode, int P)
 {
@@ -308,6 +442,10 @@ static int fir_dispatch(const b200dsp_fir_plan_impl *p, int dtype, const void *x
             return launch_fir_tc_real(mode, P, x, hist, y, n, hist_len, p->tcr_mat[mode][P],
                                       p->tcr_sb[mode][P], p->ntaps, p->sm_count, s);
         }
+        if (L > 1 && v != 8 && v != 9) {       // few taps per phase: short-phase kernel (v == 8 / 9: fir_poly_kernel)
+            const int rc = launch_fir_up_short<float, 8>(p, x, hist, y, n, L, hist_len, s);
+            if (rc != B200DSP_E_UNSUPPORTED) return rc;
+        }
         if (v == 1) return launch_fir_fit<float, 16>(p, x, hist, y, n, n_m, L, M, hist_len, s, 256);
         return launch_fir_fit<float, 32>(p, x, hist, y, n, n_m, L, M, hist_len, s, 128);
     case B200DSP_C64:
@@ -323,6 +461,10 @@ static int fir_dispatch(const b200dsp_fir_plan_impl *p, int dtype, const void *x
                 return launch_fir_tc2(x, hist, y, n, hist_len, p->tc2_amat, p->tc2_sb_exp, p->ntaps,
                                       v == 13 ? 128 : (v == 12 ? 64 : (v == 15 ? 80 : 96)), p->sm_count, s);
         }
+        if (L > 1 && v != 8 && v != 9) {
+            const int rc = launch_fir_up_short<float2, 8, true>(p, x, hist, y, n, L, hist_len, s);
+            if (rc != B200DSP_E_UNSUPPORTED) return rc;
+        }
         if (v == 1) return launch_fir_fit<float2, 16>(p, x, hist, y, n, n_m, L, M, hist_len, s, 256);
         if (v == 2) return launch_fir_fit<float2, 16>(p, x, hist, y, n, n_m, L, M, hist_len, s, 128);
         if (v == 3) return launch_fir_fit<float2, 32>(p, x, hist, y, n, n_m, L, M, hist_len, s, 128);
@@ -331,8 +473,16 @@ static int fir_dispatch(const b200dsp_fir_plan_impl *p, int dtype, const void *x
         // default: 32 outputs/thread, packed FFMA2 (fastest CUDA-core variant measured on B200)
         return launch_fir_fit<float2, 32, true>(p, x, hist, y, n, n_m, L, M, hist_len, s, 128);
     case B200DSP_F64:
+        if (L > 1 && v != 8 && v != 9) {
+            const int rc = launch_fir_up_short<double, 4>(p, x, hist, y, n, L, hist_len, s);
+            if (rc != B200DSP_E_UNSUPPORTED) return rc;
+        }
         return launch_fir_fit<double, 16>(p, x, hist, y, n, n_m, L, M, hist_len, s, 128);
     case B200DSP_C128:
+        if (L > 1 && v != 8 && v != 9) {
+            const int rc = launch_fir_up_short<double2, 4>(p, x, hist, y, n, L, hist_len, s);
+            if (rc != B200DSP_E_UNSUPPORTED) return rc;
+        }
         return launch_fir_fit<double2, 8>(p, x, hist, y, n, n_m, L, M, hist_len, s, 128);
     default:
         set_error("fir: bad dtype code %d", dtype);

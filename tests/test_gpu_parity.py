@@ -614,3 +614,54 @@ def test_host_pipeline_equals_device_path(mods, filters):
     x64 = torch.randn((1 << 20) + 77, dtype=torch.float64).pin_memory()
     y_host = hostpipe.fir_filter_host(plan, x64, chunk=1 << 18)
     assert torch.equal(y_host, _engine.fir_filter(plan, x64.cuda()).cpu())
+
+
+# ---------------------------------------------------------------- short-phase up kernel (pulse shaping shapes)
+
+@pytest.mark.parametrize("dt", ["float32", "complex64", "float64", "complex128"])
+@pytest.mark.parametrize("fname,L", [("b33_remez_bpf", 4), ("b101", 8), ("b101", 12), ("b256", 8),
+                                     ("b256", 16), ("b7", 2), ("b7", 8), ("b1", 4), ("b101", 6)])
+def test_fir_up_short_phase_kernel(filters, fname, L, dt):
+    """up(L) with few taps per phase (fir_up_short_kernel where L*sizeof(sample) % 16 == 0, else the
+    polyphase kernel): oracle parity, overlap-save halo == monolithic bit for bit, and agreement with the
+    polyphase kernel forced through variant 8."""
+    from sk_dsp_comm_b200 import _engine, _cabi
+    b = filters[fname]
+    plan = _engine.FirPlan(b)
+    rng = np.random.default_rng(L * 131 + len(b))
+    n = 10007
+    x = rng.standard_normal(n)
+    if "complex" in dt:
+        x = x + 1j * rng.standard_normal(n)
+    x = x.astype(dt)
+    xt = torch.from_numpy(x).cuda()
+    tol = FIR_TOL32 if dt in ("float32", "complex64") else FIR_TOL64
+    y = _engine.fir_up(plan, xt, L)
+    assert y.shape == (n * L,)
+    err, scale = _maxerr(y.cpu().numpy(), oracle.fir_up(b, x, L, backend="c"))
+    assert err <= tol * scale, (fname, L, dt, err, scale)
+    hl = plan.up_hist_len(L)
+    for cut in (hl, 256, 4001):
+        if cut < hl:
+            continue
+        y2 = _engine.fir_up(plan, xt[cut:].contiguous(), L, hist=xt[cut - hl:cut].contiguous())
+        assert torch.equal(y[L * cut:], y2), (fname, L, dt, cut)
+    _cabi.lib.b200dsp_set_fir_variant(8)
+    try:
+        yp = _engine.fir_up(plan, xt, L)
+    finally:
+        _cabi.lib.b200dsp_set_fir_variant(0)
+    assert float((yp - y).abs().max()) <= 2 * tol * scale
+
+
+def test_fir_up_short_phase_long_stream(filters):
+    """2^22 complex64 symbols, 8 samples/symbol, 97-tap pulse: whole output against the oracle."""
+    from sk_dsp_comm_b200 import _engine
+    rng = np.random.default_rng(77)
+    n, L = (1 << 22) + 3, 8
+    k = np.arange(-48, 49) / 8.0
+    b = np.sinc(k) * np.hamming(97)
+    x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    y = _engine.fir_up(_engine.FirPlan(b), torch.from_numpy(x).cuda(), L).cpu().numpy()
+    err, scale = _maxerr(y, oracle.fir_up(b, x, L, backend="c"))
+    assert err <= FIR_TOL32 * scale, (err, scale)

@@ -5,7 +5,7 @@ import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "scikit-dsp-comm_b200")]
 import numpy as np, torch
-from sk_dsp_comm_b200 import _engine, _pulse
+from sk_dsp_comm_b200 import _engine, _pulse, _cabi
 import sk_dsp_comm_b200.digitalcom as dc
 import sk_dsp_comm_b200.multirate_helper as mrh
 pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -34,6 +34,20 @@ for dt, esz in ((torch.complex128, 16), (torch.complex64, 8), (torch.float32, 4)
     y = torch.empty(n * ns, dtype=dt, device="cuda")
     report("pulse shaping SRC 97 taps ns=8 %s 2^24 symbols" % str(dt).split(".")[1], n, esz * n * (1 + ns),
            timeit(lambda: _engine.fir_up(plan, s, ns, out=y)))
+    _cabi.lib.b200dsp_set_fir_variant(8)
+    report("  same, polyphase kernel (variant 8)", n, esz * n * (1 + ns), timeit(lambda: _engine.fir_up(plan, s, ns, out=y)))
+    _cabi.lib.b200dsp_set_fir_variant(0)
+    del s, y
+b256 = np.load(os.path.join(ROOT, "tests/golden/filters.npz"))["b256"]
+p256 = _engine.FirPlan(b256)
+for L in (8, 12, 16):
+    n = 1 << 23
+    s = torch.randn(n, dtype=torch.complex64, device="cuda")
+    y = torch.empty(n * L, dtype=torch.complex64, device="cuda")
+    report("fir256 up%d complex64 2^23 (default)" % L, n, 8 * n * (1 + L), timeit(lambda: _engine.fir_up(p256, s, L, out=y)))
+    _cabi.lib.b200dsp_set_fir_variant(8)
+    report("  same, polyphase kernel (variant 8)", n, 8 * n * (1 + L), timeit(lambda: _engine.fir_up(p256, s, L, out=y)))
+    _cabi.lib.b200dsp_set_fir_variant(0)
     del s, y
 # stateful FIR block call (zi/zf): the kernel + the K-1 state bookkeeping, device tensors
 fir = mrh.multirate_FIR(np.load(os.path.join(ROOT, "tests/golden/filters.npz"))["b256"])
