@@ -81,22 +81,6 @@ class _SosRunner(object):
         return st.finish(_engine.sos_filter(self._plan, st.tensor.contiguous(), M=M_change))
 
 
-def _fir_final_state(b, tail, zi, N):
-    """lfilter's final delay values of an FIR after N samples: ``tail`` = the last min(N, K-1)
-    inputs, ``zi`` the K-1 initial values (what is left of them after N shifts is added)."""
-    K = len(b)
-    m = len(tail)
-    zf = np.zeros(K - 1, dtype=zi.dtype)
-    rev = tail[::-1]                                  # rev[j] = x[N-1-j]
-    for i in range(K - 1):
-        nj = min(K - 1 - i, m)
-        if nj:
-            zf[i] = np.dot(b[i + 1:i + 1 + nj], rev[:nj])
-    if N < K - 1:
-        zf[:K - 1 - N] += zi[N:]
-    return zf
-
-
 class rate_change(object):
     """
     A simple class for encapsulating the upsample/filter and
@@ -190,33 +174,45 @@ class multirate_FIR(object):
         return st.finish(y)
 
     def _filter_stateful(self, x, zi):
-        """lfilter's transposed-direct-form state for an FIR: with zero input the state simply
-        drains, ``y[n] += zi[n]`` for ``n < K-1``, and the final state is the tail of the
-        convolution that has not left the filter yet,
-        ``zf[i] = sum_{j} b[i+1+j] x[N-1-j] + zi[i+N]``  (scipy _signaltools.lfilter / _linear_filter).
-        The block itself runs in the FIR kernel; only the K-1 state values are handled here."""
+        """lfilter's transposed-direct-form state for an FIR.  With zero input the state simply drains,
+        so ``y[n] += zi[n]`` for ``n < K-1``; the final state is the filter's zero-input response after the
+        block, ``zf[i] = sum_j b[i+1+j] x[N-1-j] (+ zi[i+N])`` (scipy _signaltools.lfilter / _linear_filter)
+        -- i.e. what the FIR kernel outputs for K-1 zero samples whose history is the block's tail.  Both
+        the block and that (K-1)-sample launch run on the device; nothing is read back, so a stream of
+        blocks chained through ``zf`` never synchronises with the host."""
         _require_1d(x, "filter(zi=...)")
         K = self._plan.ntaps
         st = Staged(x)
         t = st.tensor.contiguous()
         N = t.numel()
-        z = np.asarray(zi.detach().cpu() if isinstance(zi, torch.Tensor) else zi).reshape(-1)
-        if z.size != K - 1:
+        if isinstance(zi, torch.Tensor):
+            z = zi.detach().reshape(-1)
+        else:
+            z = torch.from_numpy(np.ascontiguousarray(np.asarray(zi)).reshape(-1))
+        if z.numel() != K - 1:
             raise ValueError("Unexpected shape for zi: expected (%d,), found %s." % (K - 1, tuple(np.shape(zi))))
-        cplx = t.is_complex() or np.iscomplexobj(z)
-        z = z.astype(np.complex128 if cplx else np.float64)
-        if cplx and not t.is_complex():
+        if z.is_complex() and not t.is_complex():
             t = t.to(torch.complex64 if t.dtype == torch.float32 else torch.complex128)
+        z = z.to(device=t.device, dtype=t.dtype)
         y = _engine.fir_filter(self._plan, t) if N else t.clone()
         m = min(K - 1, N)
         if m:
-            y[:m] += torch.from_numpy(z[:m]).to(device=y.device, dtype=y.dtype)
-        # final state from the last min(N, K-1) inputs (2 KB for 256 taps) in float64 on the host
-        zf = _fir_final_state(self._plan.taps, t[N - m:].cpu().numpy().astype(z.dtype), z, N)
+            y[:m] += z[:m]
+        if K == 1:
+            zf = z.clone()
+        else:
+            if N >= K - 1:
+                tail = t[N - (K - 1):]
+            else:                       # block shorter than the filter memory: zeros stand in for x[<0]
+                tail = torch.cat([torch.zeros(K - 1 - N, dtype=t.dtype, device=t.device), t])
+            zf = _engine.fir_filter(self._plan, torch.zeros(K - 1, dtype=t.dtype, device=t.device),
+                                    hist=tail.contiguous())
+            if N < K - 1:
+                zf[:K - 1 - N] += z[N:]
         if st.kind == "numpy":
-            return st.finish(y), zf
-        zf_t = torch.from_numpy(zf)
-        return st.finish(y), (zf_t.to(t.device) if st.kind == "cuda" else zf_t)
+            # numpy streams are computed in float64 / complex128 like the reference
+            return st.finish(y), zf.cpu().numpy()
+        return st.finish(y), (zf if st.kind == "cuda" else zf.cpu())
 
     # -- reference: y = L*upsample(x,L); y = lfilter(b,[1],y)  (multirate_helper.py:112-118)
     def up(self, x, L_change=12):

@@ -41,21 +41,23 @@ class ShardedFIR:
               ordering) can be exercised without a GPU.  The product path never passes one.
     """
 
-    def __init__(self, b, group=None, compute=None):
+    def __init__(self, b, group=None, compute=None, compute_up=None, compute_dn=None):
         self.plan = _engine.FirPlan(b)
         self.group = group
         self.k1 = self.plan.ntaps - 1
         self._fir = compute or (lambda x, hist: _engine.fir_filter(self.plan, x, hist=hist))
+        self._up = compute_up or (lambda x, hist, L, out: _engine.fir_up(self.plan, x, L, hist=hist, out=out))
+        self._dn = compute_dn or (lambda x, hist, M, out: _engine.fir_dn(self.plan, x, M, hist=hist, out=out))
         self._symm = None
 
     # -- plumbing -------------------------------------------------------------------------
     def _rank_world(self):
         return dist.get_rank(self.group), dist.get_world_size(self.group)
 
-    def exchange_halo(self, x_local: torch.Tensor):
-        """Send my last K-1 samples to rank+1, receive rank-1's.  Returns (halo or None, works)."""
+    def exchange_halo(self, x_local: torch.Tensor, k=None):
+        """Send my last ``k`` (default K-1) samples to rank+1, receive rank-1's.  Returns (halo or None, works)."""
         rank, world = self._rank_world()
-        k1 = self.k1
+        k1 = self.k1 if k is None else int(k)
         if k1 == 0 or world == 1:
             return None, []
         if x_local.numel() < k1:
@@ -121,6 +123,66 @@ class ShardedFIR:
         else:
             y[:sp] = self._fir(head, halo)
         return y
+
+    # -- sharded interpolation / decimation -------------------------------------------------------
+    def _overlapped(self, x_local, k, sp, n_out, out_pos, run):
+        """Interior first (needs only local samples, overlaps the halo exchange), head after the halo
+        has landed.  ``k`` halo samples, split at input position ``sp``; ``out_pos(i)`` = first output
+        index produced by input position ``i``; ``run(segment, hist, out_view)`` fills ``out_view``."""
+        rank, world = self._rank_world()
+        n = x_local.numel()
+        y = torch.empty(n_out, dtype=x_local.dtype, device=x_local.device)
+        if world == 1 or k == 0:
+            run(x_local, None, y)
+            return y
+        on_gpu = x_local.is_cuda
+        if on_gpu:
+            comm = self._comm_stream(x_local.device)
+            cur = torch.cuda.current_stream(x_local.device)
+            comm.wait_stream(cur)
+            with torch.cuda.stream(comm):
+                halo, works = self.exchange_halo(x_local, k)
+                for w in works:
+                    w.wait()
+                ev = torch.cuda.Event()
+                ev.record(comm)
+        else:
+            halo, works = self.exchange_halo(x_local, k)
+        sp = min(sp, n)
+        if n > sp:
+            run(x_local[sp:], x_local[sp - k:sp].contiguous(), y[out_pos(sp):])
+        if on_gpu:
+            cur.wait_event(ev)
+        else:
+            for w in works:
+                w.wait()
+        if sp > 0:
+            run(x_local[:sp], halo, y[:out_pos(sp)])
+        return y
+
+    def up(self, x_local: torch.Tensor, L: int) -> torch.Tensor:
+        """This rank's ``L*n_local`` samples of ``multirate_FIR.up(x_global, L)``: the halo is the last
+        ``ceil((K-1)/L)`` INPUT samples of rank-1."""
+        L = int(L)
+        hl = self.plan.up_hist_len(L)
+        sp = (hl + 63) // 64 * 64
+        return self._overlapped(x_local, hl, sp, x_local.numel() * L, lambda i: i * L,
+                                lambda seg, hist, out: self._up(seg, hist, L, out))
+
+    def dn(self, x_local: torch.Tensor, M: int) -> torch.Tensor:
+        """This rank's ``n_local // M`` samples of ``multirate_FIR.dn(x_global, M)``.  Segment starts must
+        be multiples of ``M`` (``segment_bounds(..., align=M)``) so that decimation phase 0 is global:
+        every rank but the last must therefore hold a multiple of ``M`` samples."""
+        M = int(M)
+        rank, world = self._rank_world()
+        n = x_local.numel()
+        if rank + 1 < world and n % M:
+            raise ValueError("dn: segment length %d is not a multiple of M=%d (use segment_bounds(align=M))"
+                             % (n, M))
+        step = 64 * M
+        sp = (self.k1 + step - 1) // step * step           # multiple of M (phase) and of 64 (alignment)
+        return self._overlapped(x_local, self.k1, sp, n // M, lambda i: i // M,
+                                lambda seg, hist, out: self._dn(seg, hist, M, out))
 
     _comm_streams = {}
 

@@ -28,16 +28,27 @@ def _rel(got, want):
 # ------------------------------------------------------------------------------ CPU: host logic
 
 @pytest.mark.parametrize("c", FIRZ, ids=[c["key"] for c in FIRZ])
-def test_fir_final_state_formula(c):
-    """zf of lfilter's transposed FIR from the last K-1 inputs + what is left of zi."""
-    from sk_dsp_comm_b200.multirate_helper import _fir_final_state
+def test_fir_final_state_is_zero_input_response(c):
+    """The identity the stateful FIR call relies on: lfilter's zf == the filter's output for K-1 zero
+    samples whose history is the block's tail (+ what is left of zi when the block is shorter than K-1),
+    and y == FIR(x) with zi added to the first K-1 outputs.  Checked with the oracle on scipy's fixtures."""
+    import oracle
     k = c["key"]
     b, x, zi = F[c["filt"]], S[k + "_x"], S[k + "_zi"]
-    cplx = np.iscomplexobj(x) or np.iscomplexobj(zi)
-    dt = np.complex128 if cplx else np.float64
-    m = min(len(b) - 1, len(x))
-    zf = _fir_final_state(b, x[len(x) - m:].astype(dt), zi.astype(dt), len(x))
-    assert _rel(zf, S[k + "_zf"]) <= 1e-13 if zf.size else True
+    K, N = len(b), len(x)
+    dt = np.complex128 if (np.iscomplexobj(x) or np.iscomplexobj(zi)) else np.float64
+    x64 = x.astype(dt)
+    y = oracle.fir_filter(b, x64, backend="numpy")
+    m = min(K - 1, N)
+    y[:m] += zi[:m]
+    assert _rel(y, S[k + "_y"]) <= 1e-13
+    if K == 1:
+        return
+    tail = x64[N - (K - 1):] if N >= K - 1 else np.concatenate([np.zeros(K - 1 - N, dt), x64])
+    zf = oracle.fir_filter(b, np.zeros(K - 1, dt), hist=tail, backend="numpy")
+    if N < K - 1:
+        zf[:K - 1 - N] += zi[N:]
+    assert _rel(zf, S[k + "_zf"]) <= 1e-13
 
 
 # ------------------------------------------------------------------------------ GPU

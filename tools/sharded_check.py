@@ -33,6 +33,25 @@ try:
     assert d <= 1e-6
 except Exception as e:
     print("rank", rank, "peer-halo path unavailable:", repr(e)[:300], flush=True)
+# ---- sharded up(L) / dn(M) (halo = ceil((K-1)/L) / K-1 input samples; dn segments aligned to M) ----
+xf = np.random.default_rng(5).standard_normal(n_local * world).astype(np.float32)
+xl = torch.from_numpy(xf[rank * n_local:(rank + 1) * n_local]).to(dev)
+for L in (4, 8):
+    yu = sh.up(xl, L)
+    torch.cuda.synchronize()
+    pre = max(lo - 255, 0)
+    refu = oracle.fir_up(b, xf[pre:lo + W].astype(np.float64), L, backend="c")[(lo - pre) * L:]
+    eu = np.abs(yu[:W * L].cpu().numpy() - refu).max() / np.abs(refu).max()
+    print("rank", rank, "sharded up(%d) head window err/max %.3g" % (L, eu), flush=True)
+    assert eu <= 1e-6
+for M in (4, 8):
+    yd = sh.dn(xl, M)
+    torch.cuda.synchronize()
+    pre = max(lo - 256, 0)                     # multiple of M: decimation phase 0 stays on the global grid
+    refd = oracle.fir_dn(b, xf[pre:lo + W].astype(np.float64), M, backend="c")[(lo - pre) // M:]
+    ed = np.abs(yd[:W // M].cpu().numpy() - refd).max() / np.abs(refd).max()
+    print("rank", rank, "sharded dn(%d) head window err/max %.3g" % (M, ed), flush=True)
+    assert ed <= 1e-6
 # ---- sharded IIR (state-carry all-gather) ----
 from sk_dsp_comm_b200.sharded import ShardedIIR
 sos = np.load(os.path.join(ROOT, "tests/golden/filters.npz"))["sos6"]
