@@ -16,12 +16,11 @@ container / dtype rules.  Plot helpers (``freq_resp``, ``zplane``) are out of sc
 """
 from __future__ import annotations
 
+import warnings
 from logging import getLogger
 
 import numpy as np
 import torch
-
-import warnings
 
 from . import _design, _engine
 from ._io import Staged
