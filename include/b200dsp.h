@@ -65,14 +65,19 @@ int32_t b200dsp_fir_plan_ntaps(const b200dsp_fir_plan *plan);
 /* y[i] = sum_k b[k] * xe[i-k], i in [0,n); xe = [hist ; x].
  * Replaces multirate_FIR.filter -> signal.lfilter(self.b,[1],x)  (multirate_helper.py:104-109).
  * hist: the ntaps-1 samples preceding x (overlap-save halo of a sharded stream),
- *       or NULL for the reference's zero initial state. */
+ *       or NULL for the reference's zero initial state.  lfilter's zi/zf state is expressed through
+ *       hist as well: zf = this call on ntaps-1 zero samples with hist = the block's tail.
+ * Also replaces sigsys.os_filter / oa_filter (sigsys.py:482-598), which compute the same output
+ * through FFT frames. */
 int b200dsp_fir_filter(const b200dsp_fir_plan *plan, int dtype, const void *x, const void *hist,
                        void *y, int64_t n, void *stream);
 
 /* y[L*m+r] = L * sum_q b[L*q+r] * xe[m-q], m in [0,n): n*L outputs.
  * Replaces multirate_FIR.up -> lfilter(b,[1], L*upsample(x,L))  (multirate_helper.py:112-118)
  * without materialising the zero-stuffed stream.  hist: ceil((ntaps-1)/L) preceding input
- * samples or NULL.  Use b200dsp_fir_up_hist_len() for the exact count. */
+ * samples or NULL.  Use b200dsp_fir_up_hist_len() for the exact count.
+ * The same entry serves the reference's pulse-shaping call sites lfilter(b,1,upsample(x,ns))
+ * (digitalcom.py:488,666,1047,1676,1821; sigsys.py:2149,2201) with a plan holding b/ns. */
 int b200dsp_fir_up(const b200dsp_fir_plan *plan, int dtype, const void *x, const void *hist,
                    void *y, int64_t n, int32_t L, void *stream);
 int32_t b200dsp_fir_up_hist_len(const b200dsp_fir_plan *plan, int32_t L);
