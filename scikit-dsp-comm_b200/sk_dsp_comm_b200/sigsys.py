@@ -316,3 +316,49 @@ def oa_filter(x, h, N, mode=0):
         xk = np.hstack((xp[k * L:(k + 1) * L], np.zeros(N - L)))
         y_mat[k, k * L:k * L + N] = _run_fir(plan, xk)
     return y, y_mat[:, 0:Nx]
+
+
+# ---------------------------------------------------------------------------------------------
+# Ten-band graphic equaliser: the reference's other in-package caller of the biquad-cascade
+# arithmetic (sigsys.py:96-141, 202-252; literal known-answer vector tests/test_sigsys.py:28-34).
+# The reference chains ten ``lfilter(B_k, A_k, .)`` calls; the same ten transposed-direct-form-II
+# sections run as ONE parallel-prefix cascade launch here.
+
+def peaking(GdB, fc, Q=3.5, fs=44100.):
+    """
+    A second-order peaking filter having GdB gain at fc and approximately 0 dB otherwise
+    (reference: sigsys.py:202-252).  Returns ``b, a`` (three coefficients each, ``a[0] == 1``).
+    """
+    mu = 10 ** (GdB / 20.)
+    kq = 4 / (1 + mu) * np.tan(2 * np.pi * fc / fs / (2 * Q))
+    Cpk = (1 + kq * mu) / (1 + kq)
+    c0 = -2 * np.cos(2 * np.pi * fc / fs)
+    b = Cpk * np.array([1, c0 / (1 + kq * mu), (1 - kq * mu) / (1 + kq * mu)])
+    a = np.array([1, c0 / (1 + kq), (1 - kq) / (1 + kq)])
+    return b, a
+
+
+def ten_band_eq_filt(x, GdB, Q=3.5):
+    """
+    Filter the input signal x with a ten-band equalizer having octave gain values in ndarray GdB
+    (band centres 31.25 Hz ... 16 kHz at fs = 44.1 kHz; reference: sigsys.py:96-141).
+    """
+    NB = len(GdB)
+    if not NB == 10:
+        raise ValueError("GdB length not equal to ten")
+    Fc = 31.25 * 2 ** np.arange(NB)
+    sos = np.array([np.hstack(peaking(GdB[k], Fc[k], Q)) for k in range(NB)])
+    from .multirate_helper import _SosRunner
+    return _SosRunner(sos).filter(x)
+
+
+def cic(m, k):
+    """
+    A functional form implementation of a cascade of integrator comb (CIC) filters: the taps of
+    ``k`` cascaded length-``m`` boxcars, unity gain at DC (reference: sigsys.py:62-93).  Host-side
+    design; feed the result to ``multirate_FIR`` to run it.
+    """
+    b = np.ones(m)
+    for _ in range(1, k):
+        b = np.convolve(b, np.ones(m))
+    return b / np.sum(b)

@@ -82,6 +82,16 @@ def main():
             key = "sosz_%s_%s" % (name, tag)
             out[key + "_x"], out[key + "_zi"], out[key + "_y"], out[key + "_zf"] = x, zi, y, zf
             table.append(dict(kind="sosz", key=key, filt=name))
+    # ---- ten-band equaliser (sigsys.py:96-141): literal test input (tests/test_helper.py seed 100) + longer runs
+    np.random.seed(100)
+    out["eq_w10"] = np.random.randn(10)
+    out["eq_y10"] = ss.ten_band_eq_filt(out["eq_w10"], [g for g in range(1, 11)])
+    out["eq_x"] = rng.standard_normal(50000)
+    out["eq_gdb"] = np.array([3., -2., 0., 6., -6., 1.5, -1.5, 4., -4., 2.])
+    out["eq_y"] = ss.ten_band_eq_filt(out["eq_x"], out["eq_gdb"])
+    out["eq_y_q2"] = ss.ten_band_eq_filt(out["eq_x"][:5000], out["eq_gdb"], 2.0)
+    out["peak_b"], out["peak_a"] = ss.peaking(2.0, 500, 3.5, 44100)
+    out["cic_4_7"], out["cic_10_2"], out["cic_5_1"] = ss.cic(4, 7), ss.cic(10, 2), ss.cic(5, 1)
     out["table"] = np.array(json.dumps(table))
     out["scipy_version"] = np.array(scipy.__version__)
     np.savez_compressed(os.path.join(OUT, "stream_cases.npz"), **out)

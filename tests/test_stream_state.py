@@ -162,3 +162,30 @@ def test_gpu_block_filter_literal_golden():
     np.testing.assert_almost_equal(ss.oa_filter(x, np.ones(10), 2 ** 10), y_test)
     with pytest.raises(ValueError):
         ss.os_filter(x, np.ones(10), 8)
+
+
+# ------------------------------------------------------------------------------ ten-band equaliser
+
+def test_peaking_and_cic_designs_match_reference():
+    import sk_dsp_comm_b200.sigsys as ss
+    b, a = ss.peaking(2.0, 500, 3.5, 44100)
+    np.testing.assert_almost_equal(b, [1.00458357, -1.95961252, 0.96001185])     # tests/test_sigsys.py:42-47
+    np.testing.assert_almost_equal(a, [1., -1.95961252, 0.96459542])
+    assert np.abs(b - S["peak_b"]).max() <= 1e-15 and np.abs(a - S["peak_a"]).max() <= 1e-15
+    for (m, k) in ((4, 7), (10, 2), (5, 1)):
+        assert np.abs(ss.cic(m, k) - S["cic_%d_%d" % (m, k)]).max() <= 1e-16
+    assert np.sum(ss.cic(10, 1) - np.ones(10) / 10) == 0                          # tests/test_sigsys.py:13-19
+
+
+@pytest.mark.gpu
+def test_gpu_ten_band_equaliser():
+    import sk_dsp_comm_b200.sigsys as ss
+    y_test = [-4.23769156, 0.097137, 4.18516645, -0.54460053, 2.2257584, 1.60147407, -0.76767407, -1.95402381,
+              -1.0580526, 0.9111369]                                              # tests/test_sigsys.py:28-34
+    y = ss.ten_band_eq_filt(S["eq_w10"], [g for g in range(1, 11)])
+    np.testing.assert_almost_equal(y, y_test)
+    assert _rel(y, S["eq_y10"]) <= IIR_TOL
+    assert _rel(ss.ten_band_eq_filt(S["eq_x"], S["eq_gdb"]), S["eq_y"]) <= IIR_TOL
+    assert _rel(ss.ten_band_eq_filt(S["eq_x"][:5000], S["eq_gdb"], 2.0), S["eq_y_q2"]) <= IIR_TOL
+    with pytest.raises(ValueError, match="GdB length not equal to ten"):
+        ss.ten_band_eq_filt(S["eq_w10"], [g for g in range(1, 9)])
