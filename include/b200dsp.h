@@ -137,6 +137,10 @@ void b200dsp_launch_count_reset(void);
  * 0 = default heuristic.  Other values are documented in DESIGN.md. */
 void b200dsp_set_fir_variant(int variant);
 
+/* Same for the SOS cascade: 0 = default heuristic, 1 = force the three-kernel scan path,
+ * 2 = force the single-pass tensor-core kernel (float32) whenever the plan has its tables. */
+void b200dsp_set_sos_variant(int variant);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,6 +21,8 @@
 // Up-sampling (zero stuffing, x L gain) is fused into the chunk read and down-sampling into the
 // write (element-wise path), so multirate_IIR.up/.dn never materialise the full-rate stream.
 #include "common.cuh"
+#include "sos_tc.cuh"
+#include <type_traits>
 #include <vector>
 
 namespace b200dsp {
@@ -433,12 +435,17 @@ struct SosGroup {
     std::vector<double> tileA;         // A^(SOS_NT*SOS_LC): one tile step
     float *mats_f32;                   // device [SOS_LEVELS][D*D]: A^(SOS_LC * 2^j)
     double *mats_f64;
+    StcTables tc;                      // tensor-core single-pass kernel tables (float32 streams, sos_tc.cu)
 };
 
 struct b200dsp_sos_plan_impl {
     int nsec;
+    int sm_count;
     std::vector<SosGroup> groups;
 };
+
+// 0 auto, 1 force the 3-kernel scan path, 2 force the tensor-core kernel whenever its tables exist
+static thread_local int g_sos_variant = 0;
 
 static void matmul(const std::vector<double> &a, const std::vector<double> &b, std::vector<double> &c, int D)
 {
@@ -585,6 +592,42 @@ static bool sos_needs_tmp(size_t ngroups, int64_t n_rate, int32_t L, int32_t M)
 // Long rate-changing calls run the cascade on the vectorised full-rate path: the (L x gain) zero-stuffed
 // input or the undecimated output is staged once in the workspace by the streaming index-map kernels
 // (an IIR has to run at the full rate anyway); short calls use the fused element-wise path.
+static bool sos_tc_path(const b200dsp_sos_plan_impl *p, int dtype, int64_t n_rate, int32_t M)
+{
+    if (dtype != B200DSP_F32 || g_sos_variant == 1) return false;
+    if (M > 1 && p->groups.size() > 2) return false;      // full-rate intermediates would need two scratch streams
+    for (const SosGroup &g : p->groups)
+        if (!stc_usable(g.tc, n_rate, p->sm_count, g_sos_variant == 2)) return false;
+    return true;
+}
+
+// float32 streams whose cascade decays within a few tiles: one single-pass tensor-core launch per group of
+// <= 8 sections, zero stuffing fused into the first group's tile load and decimation into the last group's stores
+static int sos_run_tc(const b200dsp_sos_plan_impl *p, const float *x, float *y, int64_t n, int32_t L, int32_t M,
+                      const void *zi, void *zf, unsigned char *ws, cudaStream_t st)
+{
+    const int64_t n_rate = n * L, n_out = n_rate / M;
+    const size_t ng = p->groups.size();
+    float *tmp = reinterpret_cast<float *>(ws);
+    size_t sec0 = 0;
+    for (size_t gi = 0; gi < ng; ++gi) {
+        const SosGroup &g = p->groups[gi];
+        const bool first = gi == 0, last = gi + 1 == ng;
+        // ping-pong between y and the workspace so that the last group lands in y (never in place: a block's
+        // warm-up tiles are read from its neighbour's range)
+        auto out_of = [&](size_t k) -> float * { return ((ng - 1 - k) % 2 == 0 && (M == 1 || k + 1 == ng)) ? y : tmp; };
+        const float *src = first ? x : out_of(gi - 1);
+        float *dst = out_of(gi);
+        const float *zig = zi ? static_cast<const float *>(zi) + sec0 * 2 : nullptr;
+        float *zfg = zf ? static_cast<float *>(zf) + sec0 * 2 : nullptr;
+        int rc = launch_sos_tc(g.tc, src, dst, first ? n : n_rate, n_rate, last ? n_out : n_rate, first ? L : 1,
+                               last ? M : 1, zig, zfg, p->sm_count, st);
+        if (rc != B200DSP_OK) return rc;
+        sec0 += g.nsec_real;
+    }
+    return B200DSP_OK;
+}
+
 template <typename S>
 static int sos_run(const b200dsp_sos_plan_impl *p, const S *x, S *y, int64_t n, int32_t L, int32_t M,
                    const void *zi, void *zf, unsigned char *ws, int dtype, cudaStream_t st)
@@ -594,6 +637,9 @@ static int sos_run(const b200dsp_sos_plan_impl *p, const S *x, S *y, int64_t n, 
     const int64_t n_rate = n * L;
     const int64_t n_out = n_rate / M;
     const size_t ng = p->groups.size();
+    if constexpr (std::is_same<S, float>::value) {
+        if (sos_tc_path(p, dtype, n_rate, M)) return sos_run_tc(p, x, y, n, L, M, zi, zf, ws, st);
+    }
     S *tmp = nullptr;
     if (sos_needs_tmp(ng, n_rate, L, M))
         tmp = reinterpret_cast<S *>(ws + ((sos_scan_area_bytes(dtype, n_rate) + 255) & ~(size_t)255));
@@ -650,6 +696,11 @@ int b200dsp_sos_plan_create(const double *sos_host, int32_t nsec, b200dsp_sos_pl
         }
     b200dsp_sos_plan *p = new b200dsp_sos_plan();
     p->nsec = nsec;
+    p->sm_count = 148;
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, dev);
+    }
     for (int s0 = 0; s0 < nsec; s0 += SOS_MAXSEC) {
         SosGroup g;
         g.nsec_real = (nsec - s0 < SOS_MAXSEC) ? nsec - s0 : SOS_MAXSEC;
@@ -702,6 +753,7 @@ int b200dsp_sos_plan_create(const double *sos_host, int32_t nsec, b200dsp_sos_pl
             // pageable-memory cudaMemcpy may return before the DMA completes; consumers use non-blocking streams
             if (e == cudaSuccess) e = cudaStreamSynchronize(0);
         }
+        if (e == cudaSuccess && stc_build(g.coef, g.nsec, g.nsec_real, &g.tc) != B200DSP_OK) e = cudaErrorUnknown;
         p->groups.push_back(g);
         if (e != cudaSuccess) {
             set_error("sos_plan_create: %s", cudaGetErrorString(e));
@@ -719,6 +771,7 @@ void b200dsp_sos_plan_destroy(b200dsp_sos_plan *plan)
     for (auto &g : plan->groups) {
         cudaFree(g.mats_f32);
         cudaFree(g.mats_f64);
+        stc_free(&g.tc);
     }
     delete plan;
 }
@@ -762,5 +815,7 @@ int b200dsp_sos_filter(const b200dsp_sos_plan *plan, int dtype, const void *x, v
     }
     return B200DSP_E_DTYPE;
 }
+
+void b200dsp_set_sos_variant(int variant) { g_sos_variant = variant; }
 
 }  // extern "C"

@@ -18,18 +18,34 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// Bounded wait: a protocol bug must end in a trap, never in a hung GPU.
+// Bounded wait: a protocol bug must end in a trap, never in a hung GPU.  The bound is WALL-CLOCK time
+// (%globaltimer, 20 s), not a poll count, so profiler replay, preemption or MPS time-slicing cannot
+// false-trap a healthy kernel.
+__device__ __forceinline__ uint64_t global_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int who) {
-    uint32_t done = 0;
-    for (uint32_t spin = 0; spin < (1u << 27); ++spin) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (done) return;
+    uint64_t t0 = 0;
+    for (uint32_t spin = 1;; ++spin) {
+        if (mbar_try(bar, parity)) return;
+        if ((spin & 0xFFFFu) == 0) {
+            const uint64_t t = global_ns();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 20000000000ull) break;
+        }
     }
-    printf("b200dsp tensor-core FIR: mbarrier timeout (role %d, block %d)\n", who, (int)blockIdx.x);
+    printf("b200dsp tensor-core kernel: mbarrier timeout (role %d, block %d)\n", who, (int)blockIdx.x);
     __trap();
 }
 // one elected lane of a converged warp (lets ptxas emit UTCHMMA / UBLKCP without a lane loop)
@@ -69,6 +85,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
         : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }

@@ -28,6 +28,7 @@ SYMBOLS = (
     "b200dsp_sos_workspace_bytes", "b200dsp_sos_filter",
     "b200dsp_upsample", "b200dsp_downsample",
     "b200dsp_launch_count", "b200dsp_launch_count_reset", "b200dsp_set_fir_variant",
+    "b200dsp_set_sos_variant",
 )
 
 
@@ -67,6 +68,8 @@ def _load():
     lib.b200dsp_launch_count_reset.restype = None
     lib.b200dsp_set_fir_variant.argtypes = [I]
     lib.b200dsp_set_fir_variant.restype = None
+    lib.b200dsp_set_sos_variant.argtypes = [I]
+    lib.b200dsp_set_sos_variant.restype = None
     return lib
 
 
