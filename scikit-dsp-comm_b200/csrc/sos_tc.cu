@@ -50,8 +50,11 @@ constexpr int A_COLS = 192;
 constexpr int ACC_COL0 = A_COLS;
 constexpr int ACC_STRIDE = 2 * NCHUNK;        // Y | E
 // warps: a warp reads TMEM lanes 32 * (warp % 4) .. +31, so the carry readers (lanes 0..31) sit at 8 and 12
-constexpr int N_EPI_WARPS = 8, ZSCAN_WARP0 = 8, MMA_WARP = 9, CHAIN_WARP = 10, ZSCAN_WARP1 = 12;
-constexpr int N_CVT_WARPS = 4;                // converter warps: 11, 13, 14, 15
+// warp 8 (TMEM lanes 0..31) issues the TMA loads and the MMAs AND reads the carry accumulator back while the tensor
+// pipe works on the tile's output MMAs; chain and scan warps need no TMEM access and sit on the other schedulers
+// (scheduler = warp % 4), one converter warp per scheduler
+constexpr int N_EPI_WARPS = 8, MMA_WARP = 8, CHAIN_WARP = 9, ZSCAN_WARP0 = 10, ZSCAN_WARP1 = 11, CVT_WARP0 = 12;
+constexpr int N_CVT_WARPS = 4;
 constexpr int N_CVT = N_CVT_WARPS * 32;
 constexpr int NTHREADS = 16 * 32;             // 512 threads -> 128 registers per thread
 constexpr int G_PER_THREAD = TILE / 4 / N_CVT;                // 16 float4 groups per converter thread
@@ -68,7 +71,7 @@ constexpr int SM_ESM = SM_FOLD + NFOLD * FOLD_PITCH * 4;      // float [2][64][E
 constexpr int SM_S0 = SM_ESM + 2 * NCHUNK * EP * 4;           // float [2][64][EP]        zero-state -> true chunk start states
 constexpr int SM_AGG = SM_S0 + 2 * NCHUNK * EP * 4;           // double [2][16]           zero-state end state of a tile
 constexpr int SM_BAR = SM_AGG + 2 * 16 * 8;
-constexpr int NBAR = 3 * NSTAGE + 7 * NACC;
+constexpr int NBAR = 3 * NSTAGE + 9 * NACC;
 constexpr int SM_MISC = SM_BAR + NBAR * 8;                    // tmem slot, wmax[4], tile_e[16]
 constexpr int SMEM_TOTAL = SM_MISC + 128 + 1024;
 static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
@@ -199,6 +202,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
     auto S_READY = [&](int b) { return bar0 + 8u * (3 * NSTAGE + 4 * NACC + b); };
     auto S_EMPTY = [&](int b) { return bar0 + 8u * (3 * NSTAGE + 5 * NACC + b); };
     auto Z_READY = [&](int b) { return bar0 + 8u * (3 * NSTAGE + 6 * NACC + b); };
+    auto ESM_READY = [&](int b) { return bar0 + 8u * (3 * NSTAGE + 7 * NACC + b); };
+    auto ESM_EMPTY = [&](int b) { return bar0 + 8u * (3 * NSTAGE + 8 * NACC + b); };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + SM_MISC);
     float *wmax = reinterpret_cast<float *>(sm + SM_MISC + 16);
     int *tile_e = reinterpret_cast<int *>(sm + SM_MISC + 32);
@@ -212,7 +217,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
         for (int s = 0; s < NSTAGE; ++s) {
             mbar_init(RAW_FULL(s), 1);
             mbar_init(A_FULL(s), N_CVT_WARPS);
-            mbar_init(A_EMPTY(s), 1);
+            mbar_init(A_EMPTY(s), 2);                      // carry MMAs (warp 8) + output MMAs (warp 0) have read the stage
         }
         for (int b = 0; b < NACC; ++b) {
             mbar_init(E_FULL(b), 1);
@@ -222,6 +227,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
             mbar_init(S_READY(b), 1);
             mbar_init(S_EMPTY(b), N_EPI_WARPS);
             mbar_init(Z_READY(b), 1);
+            mbar_init(ESM_READY(b), 1);
+            mbar_init(ESM_EMPTY(b), 1);
         }
         fence_barrier_init();
     }
@@ -258,10 +265,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
     const int64_t t_begin = (blockIdx.x == 0) ? 0 : t_own - a.warm_tiles;
     const int64_t t_end = (t_own + a.tiles_per_block < a.n_tiles) ? t_own + a.tiles_per_block : a.n_tiles;
 
-    if (warp == 11 || warp >= 13) {
+    if (warp >= CVT_WARP0) {
         // =============================== converters ===============================
         // thread ct owns float4 groups g = ct + 128 i: stream row (ct >> 4) + 8 i, i.e. a fixed row parity
-        const int cw = (warp == 11) ? 0 : warp - 12;     // converter warp index 0..3
+        const int cw = warp - CVT_WARP0;                 // converter warp index 0..3
         const int ct = cw * 32 + lane;
         const int parity = (ct >> 4) & 1, c_first = ct >> 5, colb = (ct & 15) >> 1, sub = (ct & 1) * 8;
         int it = 0;
@@ -355,83 +362,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
             }
             __syncwarp();
         };
-        for (int pit = 0; pit < NSTAGE - 1 && t_begin + pit < t_end; ++pit) produce(t_begin + pit, pit);
-        int it = 0;
-        for (int64_t tile = t_begin; tile < t_end; ++tile, ++it) {
-            if (tile + NSTAGE - 1 < t_end) produce(tile + NSTAGE - 1, it + NSTAGE - 1);
-            const int s = it % NSTAGE;
-            const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
-            const int b = it & 1;
-            const uint32_t pb = (uint32_t)(it >> 1) & 1u;
-            const uint32_t st = base + s * STAGE_BYTES;
-            const uint32_t acc = tmem_base + ACC_COL0 + b * ACC_STRIDE;
-            // operand regions of the stage: (row parity, part) -> 2 * parity + part
-            const uint64_t xe_hi = make_desc_sw128(st + 0 * REGION), xe_lo = make_desc_sw128(st + 1 * REGION);
-            const uint64_t xo_hi = make_desc_sw128(st + 2 * REGION), xo_lo = make_desc_sw128(st + 3 * REGION);
-            STC_WAIT(A_FULL(s), ph, 2);
-            STC_WAIT(E_EMPTY(b), pb ^ 1u, 3);
-            tc_fence_after();
-            if (elect_one()) {
-              if (!(DBG && (a.dbg & 1))) {
-                // chunk carries first (the scan is the serial chain): rows = states, fp16 hi rows in lanes 0-15 and
-                // their residuals in lanes 16-31; residual (lo) stream parts before the hi parts
-                const uint32_t ea = acc + NCHUNK;
-#pragma unroll
-                for (int sl = 0; sl < 4; ++sl) umma_f16_ts(ea, tmem_base + COL_KA + sl * 8, xe_lo + (uint64_t)(2 * sl), kIdesc, sl > 0);
-#pragma unroll
-                for (int sl = 0; sl < 4; ++sl) umma_f16_ts(ea, tmem_base + COL_KB + sl * 8, xo_lo + (uint64_t)(2 * sl), kIdesc, 1);
-#pragma unroll
-                for (int sl = 0; sl < 4; ++sl) umma_f16_ts(ea, tmem_base + COL_KA + sl * 8, xe_hi + (uint64_t)(2 * sl), kIdesc, 1);
-#pragma unroll
-                for (int sl = 0; sl < 4; ++sl) umma_f16_ts(ea, tmem_base + COL_KB + sl * 8, xo_hi + (uint64_t)(2 * sl), kIdesc, 1);
-              }
-              umma_commit(E_FULL(b));         // commit from the issuing thread: it tracks THAT thread's MMAs
-            }
-            __syncwarp();
-            STC_WAIT(D_EMPTY(b), pb ^ 1u, 4);
-            tc_fence_after();
-            if (elect_one()) {
-              if (!(DBG && (a.dbg & 1))) {
-                // zero-state outputs: rows = the 128 positions of a chunk, K = the chunk's 128 samples (even row
-                // then odd row); three partial products, smallest first: T_hi x_lo, T_lo x_hi, T_hi x_hi
-#pragma unroll
-                for (int sl = 0; sl < 8; ++sl)
-                    umma_f16_ts(acc, tmem_base + COL_THI + sl * 8, (sl < 4 ? xe_lo : xo_lo) + (uint64_t)(2 * (sl & 3)), kIdesc, sl > 0);
-#pragma unroll
-                for (int sl = 0; sl < 8; ++sl)
-                    umma_f16_ts(acc, tmem_base + COL_TLO + sl * 8, (sl < 4 ? xe_hi : xo_hi) + (uint64_t)(2 * (sl & 3)), kIdesc, 1);
-#pragma unroll
-                for (int sl = 0; sl < 8; ++sl)
-                    umma_f16_ts(acc, tmem_base + COL_THI + sl * 8, (sl < 4 ? xe_hi : xo_hi) + (uint64_t)(2 * (sl & 3)), kIdesc, 1);
-              }
-              umma_commit(D_FULL(b));
-              umma_commit(A_EMPTY(s));
-            }
-            __syncwarp();
-        }
-    } else if (warp == ZSCAN_WARP0 || warp == ZSCAN_WARP1) {
-        // =============================== carries -> zero-state chunk start states ===============================
-        // Two warps take alternate tiles (warp b owns accumulator buffer b).  Everything here is independent of the
-        // state entering the tile, so it is OFF the serial chain between tiles; float64 throughout.
-        // Z64: float64 arithmetic (plans whose cascade decays slowly: the state is ill-conditioned against the
-        // output); otherwise float32 -- the scan covers one tile from zero state, nothing accumulates across tiles.
-        using ZT = typename std::conditional<Z64, double, float>::type;
-        const int b = (warp == ZSCAN_WARP0) ? 0 : 1;
-        const ZT *MA128, *MKS;                            // A^128 and A^256, A^512 ... (column-major)
-        int mstride;
-        if constexpr (Z64) { MA128 = smat; MKS = smat + ND * ND; mstride = ND * ND; }
-        else { MA128 = fold + 12 * FOLD_PITCH; MKS = fold + 13 * FOLD_PITCH; mstride = FOLD_PITCH; }
+        // carry accumulator (TMEM lanes 0-15: fp16-hi rows of the states, 16-31: their residual rows) -> sum, unscale,
+        // transpose through shared memory into one row per chunk for the scan warps
         const bool lo_row = lane >= 16;
         const int d = lane & 15;
         const float rowinv = a.rowinv[d];
-        float *es = esm + b * NCHUNK * EP;
-        int it = b;
-        for (int64_t tile = t_begin + b; tile < t_end; tile += 2, it += 2) {
-            const uint32_t pb = (uint32_t)(it >> 1) & 1u;
-            STC_WAIT(E_FULL(b), pb, 5);
+        auto eread = [&](int eit) {
+            const int eb = eit & 1;
+            const uint32_t epb = (uint32_t)(eit >> 1) & 1u;
+            STC_WAIT(ESM_EMPTY(eb), epb ^ 1u, 3);
+            STC_WAIT(E_FULL(eb), epb, 4);
             tc_fence_after();
-            const float sc = ldexpf(rowinv, -tile_e[it % E_RING]);
-            const uint32_t eaddr = tmem_base + ACC_COL0 + b * ACC_STRIDE + NCHUNK;     // TMEM lanes 0..31
+            float *es = esm + eb * NCHUNK * EP;
+            const float sc = ldexpf(rowinv, -tile_e[eit % E_RING]);
+            const uint32_t eaddr = tmem_base + ACC_COL0 + eb * ACC_STRIDE + NCHUNK;     // TMEM lanes 0..31
 #pragma unroll 1
             for (int c0 = 0; c0 < NCHUNK; c0 += 16) {        // rolled: keeps the role's code inside the instruction cache
                 uint32_t v[16];
@@ -447,8 +391,78 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(E_EMPTY(b));
+            if (lane == 0) {
+                mbar_arrive(E_EMPTY(eb));
+                mbar_arrive(ESM_READY(eb));
+            }
             __syncwarp();
+        };
+        // carry MMAs of tile eit: rows = states (fp16 hi rows in TMEM lanes 0-15, residual rows in 16-31),
+        // residual (lo) stream parts before the hi parts
+        auto issue_e = [&](int eit) {
+            const int s = eit % NSTAGE;
+            const int eb = eit & 1;
+            const uint32_t st = base + s * STAGE_BYTES;
+            const uint64_t xe_hi = make_desc_sw128(st + 0 * REGION), xe_lo = make_desc_sw128(st + 1 * REGION);
+            const uint64_t xo_hi = make_desc_sw128(st + 2 * REGION), xo_lo = make_desc_sw128(st + 3 * REGION);
+            STC_WAIT(A_FULL(s), (uint32_t)(eit / NSTAGE) & 1u, 2);
+            STC_WAIT(E_EMPTY(eb), ((uint32_t)(eit >> 1) & 1u) ^ 1u, 3);
+            tc_fence_after();
+            if (elect_one()) {
+                if (!(DBG && (a.dbg & 1))) {
+                    const uint32_t ea = tmem_base + ACC_COL0 + eb * ACC_STRIDE + NCHUNK;
+#pragma unroll
+                    for (int sl = 0; sl < 4; ++sl) umma_f16_ts(ea, tmem_base + COL_KA + sl * 8, xe_lo + (uint64_t)(2 * sl), kIdesc, sl > 0);
+#pragma unroll
+                    for (int sl = 0; sl < 4; ++sl) umma_f16_ts(ea, tmem_base + COL_KB + sl * 8, xo_lo + (uint64_t)(2 * sl), kIdesc, 1);
+#pragma unroll
+                    for (int sl = 0; sl < 4; ++sl) umma_f16_ts(ea, tmem_base + COL_KA + sl * 8, xe_hi + (uint64_t)(2 * sl), kIdesc, 1);
+#pragma unroll
+                    for (int sl = 0; sl < 4; ++sl) umma_f16_ts(ea, tmem_base + COL_KB + sl * 8, xo_hi + (uint64_t)(2 * sl), kIdesc, 1);
+                }
+                umma_commit(E_FULL(eb));         // commit from the issuing thread: it tracks THAT thread's MMAs
+                umma_commit(A_EMPTY(s));
+            }
+            __syncwarp();
+        };
+        // The carry path (this warp -> scan warps -> chain warp) never waits for the output path (the output MMAs are
+        // issued by epilogue warp 0).  Loads: a tile's stage must be requested before its A_FULL is awaited (blocking);
+        // beyond that the ring is topped up opportunistically (non-blocking probe of the stage barrier).
+        const int n_it = (int)(t_end - t_begin);
+        int next_prod = 0;
+        auto top_up = [&](int need) {
+            while (next_prod < n_it) {
+                const int ps = next_prod % NSTAGE;
+                const uint32_t par = ((uint32_t)(next_prod / NSTAGE) & 1u) ^ 1u;
+                if (next_prod > need && (next_prod >= need + NSTAGE || !mbar_test(A_EMPTY(ps), par))) break;
+                produce(t_begin + next_prod, next_prod);
+                ++next_prod;
+            }
+        };
+        top_up(0);
+        if (n_it > 0) issue_e(0);
+        for (int it = 0; it < n_it; ++it) {
+            top_up(it + 1);
+            if (it + 1 < n_it) issue_e(it + 1);            // the tensor pipe works on the next tile's carries ...
+            eread(it);                                     // ... while this warp reads the current ones back
+        }
+    } else if (warp == ZSCAN_WARP0 || warp == ZSCAN_WARP1) {
+        // =============================== carries -> zero-state chunk start states ===============================
+        // Two warps take alternate tiles (warp b owns accumulator buffer b).  Everything here is independent of the
+        // state entering the tile, so it is OFF the serial chain between tiles; float64 throughout.
+        // Z64: float64 arithmetic (plans whose cascade decays slowly: the state is ill-conditioned against the
+        // output); otherwise float32 -- the scan covers one tile from zero state, nothing accumulates across tiles.
+        using ZT = typename std::conditional<Z64, double, float>::type;
+        const int b = (warp == ZSCAN_WARP0) ? 0 : 1;
+        const ZT *MA128, *MKS;                            // A^128 and A^256, A^512 ... (column-major)
+        int mstride;
+        if constexpr (Z64) { MA128 = smat; MKS = smat + ND * ND; mstride = ND * ND; }
+        else { MA128 = fold + 12 * FOLD_PITCH; MKS = fold + 13 * FOLD_PITCH; mstride = FOLD_PITCH; }
+        const float *es = esm + b * NCHUNK * EP;
+        int it = b;
+        for (int64_t tile = t_begin + b; tile < t_end; tile += 2, it += 2) {
+            const uint32_t pb = (uint32_t)(it >> 1) & 1u;
+            STC_WAIT(ESM_READY(b), pb, 5);
             // lane l owns chunks 2l, 2l+1
             ZT q[ND], o[ND], zs[ND];
             const float *e0 = es + (2 * lane) * EP, *e1 = e0 + EP;
@@ -507,7 +521,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(Z_READY(b));
+            if (lane == 0) {
+                mbar_arrive(Z_READY(b));
+                mbar_arrive(ESM_EMPTY(b));
+            }
         }
     } else if (warp == CHAIN_WARP) {
         // =============================== serial chain between tiles ===============================
@@ -522,8 +539,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
         const float *Ph = fold + (lane >> 2) * FOLD_PITCH, *Qm = fold + (8 + (lane & 3)) * FOLD_PITCH;
         const float *F128 = fold + 12 * FOLD_PITCH;
         const double *MAT = smat + 6 * ND * ND;            // A^8192
-        int it = 0;
-        for (int64_t tile = t_begin; tile < t_end; ++tile, ++it) {
+        // epilogue warp 0 also issues the output MMAs of tile it+2 as soon as tile it has left its accumulator: zero-state
+        // outputs, rows = the 128 positions of a chunk, K = the chunk's 128 samples (even row then odd row); three
+        // partial products, smallest first: T_hi x_lo, T_lo x_hi, T_hi x_hi
+        auto issue_y = [&](int yit) {
+            const int s = yit % NSTAGE;
+            const int yb = yit & 1;
+            const uint32_t st = base + s * STAGE_BYTES;
+            const uint32_t acc = tmem_base + ACC_COL0 + yb * ACC_STRIDE;
+            const uint64_t xe_hi = make_desc_sw128(st + 0 * REGION), xe_lo = make_desc_sw128(st + 1 * REGION);
+            const uint64_t xo_hi = make_desc_sw128(st + 2 * REGION), xo_lo = make_desc_sw128(st + 3 * REGION);
+            STC_WAIT(D_EMPTY(yb), ((uint32_t)(yit >> 1) & 1u) ^ 1u, 4);
+            STC_WAIT(A_FULL(s), (uint32_t)(yit / NSTAGE) & 1u, 2);
+            tc_fence_after();
+            if (elect_one()) {
+                if (!(DBG && (a.dbg & 1))) {
+#pragma unroll
+                    for (int sl = 0; sl < 8; ++sl)
+                        umma_f16_ts(acc, tmem_base + COL_THI + sl * 8, (sl < 4 ? xe_lo : xo_lo) + (uint64_t)(2 * (sl & 3)), kIdesc, sl > 0);
+#pragma unroll
+                    for (int sl = 0; sl < 8; ++sl)
+                        umma_f16_ts(acc, tmem_base + COL_TLO + sl * 8, (sl < 4 ? xe_hi : xo_hi) + (uint64_t)(2 * (sl & 3)), kIdesc, 1);
+#pragma unroll
+                    for (int sl = 0; sl < 8; ++sl)
+                        umma_f16_ts(acc, tmem_base + COL_THI + sl * 8, (sl < 4 ? xe_hi : xo_hi) + (uint64_t)(2 * (sl & 3)), kIdesc, 1);
+                }
+                umma_commit(D_FULL(yb));
+                umma_commit(A_EMPTY(s));
+            }
+            __syncwarp();
+        };
+        const int n_it = (int)(t_end - t_begin);
+        for (int it = -2; it < n_it; ++it) {
+            if (it < 0) {
+                if (warp == 0 && it + 2 < n_it) issue_y(it + 2);
+                continue;
+            }
+            const int64_t tile = t_begin + it;
             const int b = it & 1;
             const uint32_t pb = (uint32_t)(it >> 1) & 1u;
             float sf[ND], u[ND], h0[ND], h1[ND];
@@ -593,8 +645,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
         for (int k = 0; k < ND; ++k) ot[k] = a.otab[rho * 16 + k];
         const uint32_t lane_sel = (uint32_t)(qd * 32) << 16;
         const int colbase = half * 32;
-        int it = 0;
-        for (int64_t tile = t_begin; tile < t_end; ++tile, ++it) {
+        // epilogue warp 0 also issues the output MMAs of tile it+2 as soon as tile it has left its accumulator: zero-state
+        // outputs, rows = the 128 positions of a chunk, K = the chunk's 128 samples (even row then odd row); three
+        // partial products, smallest first: T_hi x_lo, T_lo x_hi, T_hi x_hi
+        auto issue_y = [&](int yit) {
+            const int s = yit % NSTAGE;
+            const int yb = yit & 1;
+            const uint32_t st = base + s * STAGE_BYTES;
+            const uint32_t acc = tmem_base + ACC_COL0 + yb * ACC_STRIDE;
+            const uint64_t xe_hi = make_desc_sw128(st + 0 * REGION), xe_lo = make_desc_sw128(st + 1 * REGION);
+            const uint64_t xo_hi = make_desc_sw128(st + 2 * REGION), xo_lo = make_desc_sw128(st + 3 * REGION);
+            STC_WAIT(D_EMPTY(yb), ((uint32_t)(yit >> 1) & 1u) ^ 1u, 4);
+            STC_WAIT(A_FULL(s), (uint32_t)(yit / NSTAGE) & 1u, 2);
+            tc_fence_after();
+            if (elect_one()) {
+                if (!(DBG && (a.dbg & 1))) {
+#pragma unroll
+                    for (int sl = 0; sl < 8; ++sl)
+                        umma_f16_ts(acc, tmem_base + COL_THI + sl * 8, (sl < 4 ? xe_lo : xo_lo) + (uint64_t)(2 * (sl & 3)), kIdesc, sl > 0);
+#pragma unroll
+                    for (int sl = 0; sl < 8; ++sl)
+                        umma_f16_ts(acc, tmem_base + COL_TLO + sl * 8, (sl < 4 ? xe_hi : xo_hi) + (uint64_t)(2 * (sl & 3)), kIdesc, 1);
+#pragma unroll
+                    for (int sl = 0; sl < 8; ++sl)
+                        umma_f16_ts(acc, tmem_base + COL_THI + sl * 8, (sl < 4 ? xe_hi : xo_hi) + (uint64_t)(2 * (sl & 3)), kIdesc, 1);
+                }
+                umma_commit(D_FULL(yb));
+                umma_commit(A_EMPTY(s));
+            }
+            __syncwarp();
+        };
+        const int n_it = (int)(t_end - t_begin);
+        for (int it = -2; it < n_it; ++it) {
+            if (it < 0) {
+                if (warp == 0 && it + 2 < n_it) issue_y(it + 2);
+                continue;
+            }
+            const int64_t tile = t_begin + it;
             const int b = it & 1;
             const uint32_t pb = (uint32_t)(it >> 1) & 1u;
             STC_WAIT(D_FULL(b), pb, 7);
@@ -631,23 +718,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
                     __syncwarp();
                     if (lane == 0) mbar_arrive(D_EMPTY(b));
                 }
+                // correction y += (C A^rho) . S_c : state index outer, chunk inner -> 8 independent FMA chains and the
+                // shared-memory loads (all lanes read the same address: broadcast) issued back to back
+                float acc[8];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    float yv = __uint_as_float(dv[c]) * inv;
-                    if (!(DBG && (a.dbg & 16))) {
+                for (int c = 0; c < 8; ++c) acc[c] = __uint_as_float(dv[c]) * inv;
+                if (!(DBG && (a.dbg & 16))) {
 #pragma unroll
-                        for (int k = 0; k < ND; k += 4) {
+                    for (int k = 0; k < ND; k += 4) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
                             const float4 sv = *reinterpret_cast<const float4 *>(s0 + c * EP + k);
-                            yv = fmaf(ot[k], sv.x, yv);
-                            yv = fmaf(ot[k + 1], sv.y, yv);
-                            yv = fmaf(ot[k + 2], sv.z, yv);
-                            yv = fmaf(ot[k + 3], sv.w, yv);
+                            acc[c] = fmaf(ot[k], sv.x, acc[c]);
+                            acc[c] = fmaf(ot[k + 1], sv.y, acc[c]);
+                            acc[c] = fmaf(ot[k + 2], sv.z, acc[c]);
+                            acc[c] = fmaf(ot[k + 3], sv.w, acc[c]);
                         }
                     }
-                    if (a.M == 1) {
-                        if (p + c * LC < limit) yp[c * LC] = yv;
-                    } else {
-                        if (r == 0 && p + c * LC < limit && m < a.n_out) a.y[m] = yv;
+                }
+                if (a.M == 1) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        if (p + c * LC < limit) yp[c * LC] = acc[c];
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        if (r == 0 && p + c * LC < limit && m < a.n_out) a.y[m] = acc[c];
                         m += step_m;
                         r += step_r;
                         if (r >= a.M) { r -= a.M; ++m; }
@@ -660,6 +756,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
             __syncwarp();
             if (DBG) ph_b += clock64() - tp0;
             if (lane == 0) mbar_arrive(S_EMPTY(b));
+            if (warp == 0 && it + 2 < n_it) issue_y(it + 2);
         }
     }
     if (DBG && (a.dbg & 8) && blockIdx.x == 1 && lane == 0)
