@@ -14,8 +14,10 @@
 //          recurrence per sample is gone: cost per sample is independent of the number of sections.
 //   prefix scan         s_{c+1} = A^128 s_c + E_c    one warp, lane = two chunks, float64 Kogge-Stone with the
 //                                                    constant matrices A^(256 * 2^j) in shared memory
-//   correction          y[n] += (C A^n) s_c          12-16 fp32 FMAs per sample in the epilogue (the row C A^n is a
-//                                                    per-lane constant because a TMEM lane IS a chunk position)
+//   correction          Y += O S                     O[r,:] = C A^r (zero-input response rows), S[:,c] = state at the start
+//                                                    of chunk c: one more K=16 GEMM step into the SAME accumulator
+//                                                    (fp16 hi/lo, three partial products), so the epilogue only scales
+//                                                    and stores
 //
 // Every CTA owns a CONTIGUOUS run of tiles, so the carry between tiles never leaves the CTA and there is no
 // grid-wide scan, no second pass and no inter-CTA traffic: x is read once, y written once (8 B/sample).  A
@@ -42,11 +44,11 @@ constexpr int TILE = NCHUNK * LC;             // 8192
 static_assert(TILE == STC_TILE, "tile size");
 constexpr int REGION = NCHUNK * BK * 2;       // one fp16 operand region: 64 rows x 128 B
 constexpr int STAGE_BYTES = 4 * REGION;       // (even,odd) x (hi,lo) = the raw fp32 tile, converted in place
-constexpr int NSTAGE = 5;
+constexpr int NSTAGE = 4;
 constexpr int NACC = 2;
-// TMEM columns: T_hi (128 rows x 128 k -> 64 columns) | T_lo (64) | Ka (32) | Kb (32) | accumulators
-constexpr int COL_THI = 0, COL_TLO = 64, COL_KA = 128, COL_KB = 160;
-constexpr int A_COLS = 192;
+// TMEM columns: T_hi (128 rows x 128 k -> 64 columns) | T_lo (64) | Ka (32) | Kb (32) | O_hi (8) | O_lo (8) | accumulators
+constexpr int COL_THI = 0, COL_TLO = 64, COL_KA = 128, COL_KB = 160, COL_OHI = 192, COL_OLO = 200;
+constexpr int A_COLS = 208;
 constexpr int ACC_COL0 = A_COLS;
 constexpr int ACC_STRIDE = 2 * NCHUNK;        // Y | E
 // warps: a warp reads TMEM lanes 32 * (warp % 4) .. +31, so the carry readers (lanes 0..31) sit at 8 and 12
@@ -64,23 +66,26 @@ constexpr int NSMAT = 7;                      // A^128, A^256, ... A^8192 (float
 constexpr int NFOLD = 18;                     // float32 matrices: A^(1024 h) h<8 | A^(256 l) l<4 | A^128 | A^256 .. A^4096
 constexpr int FOLD_PITCH = 260;               // floats per fold matrix (= 4 mod 32: distinct matrices, distinct banks)
 
+constexpr int MAXWIN = 8;                     // tiles of input history that bound the state (window of the block scale)
+constexpr int SOP_BYTES = NCHUNK * 128;       // chunk start states as an MMA operand: 64 rows x (16 hi | 16 lo | pad) fp16
+
 // shared memory map (offsets from the 1024-aligned base)
-constexpr int SM_SMAT = NSTAGE * STAGE_BYTES;                 // double [7][16*16]
+constexpr int SM_SOP = NSTAGE * STAGE_BYTES;                  // [2][SOP_BYTES]           K-major SWIZZLE_128B, 1024-aligned
+constexpr int SM_SMAT = SM_SOP + 2 * SOP_BYTES;               // double [7][16*16]
 constexpr int SM_FOLD = SM_SMAT + NSMAT * 256 * 8;            // float [18][FOLD_PITCH]
-constexpr int SM_ESM = SM_FOLD + NFOLD * FOLD_PITCH * 4;      // float [2][64][EP]        carries, private to zscan warp b
-constexpr int SM_S0 = SM_ESM + 2 * NCHUNK * EP * 4;           // float [2][64][EP]        zero-state -> true chunk start states
+constexpr int SM_ESM = SM_FOLD + NFOLD * FOLD_PITCH * 4;      // float [2][64][EP]        carries (warp 8 -> scan warp b)
+constexpr int SM_S0 = SM_ESM + 2 * NCHUNK * EP * 4;           // float [2][64][EP]        zero-state chunk start states (scan -> chain)
 constexpr int SM_AGG = SM_S0 + 2 * NCHUNK * EP * 4;           // double [2][16]           zero-state end state of a tile
 constexpr int SM_BAR = SM_AGG + 2 * 16 * 8;
-constexpr int NBAR = 3 * NSTAGE + 9 * NACC;
-constexpr int SM_MISC = SM_BAR + NBAR * 8;                    // tmem slot, wmax[4], tile_e[16]
-constexpr int SMEM_TOTAL = SM_MISC + 128 + 1024;
+constexpr int NBAR = 3 * NSTAGE + 10 * NACC;
+constexpr int SM_MISC = SM_BAR + NBAR * 8;                    // tmem slot, wmax[4], tile_e[16], tile_m[16]
+constexpr int SMEM_TOTAL = SM_MISC + 256 + 1024;
 static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
 
 struct Args {
     const float *x;
     float *y;
     const uint4 *amat;
-    const float *otab;
     const double *smat;
     const float *fold;
     const float *rowinv;
@@ -91,6 +96,9 @@ struct Args {
     int32_t L, M;
     int32_t tiles_per_block, warm_tiles;
     int32_t e_t, d_real;
+    int32_t xexp, win;        // block scale: window max of |x| over `win` tiles is scaled into [2^(xexp-1), 2^xexp)
+    float sfac[16];           // state d enters the correction operand as s_d * sfac[d] * 2^e_x
+    float ginv[16];           // 1 / (power-of-two bound of the input->state gain): |s_d| * ginv[d] <= max |x|
     int32_t nlev;             // Kogge-Stone levels whose matrix A^(256 * 2^j) is not negligible
     int32_t at_zero;          // A^8192 is negligible: the state entering a tile is the previous tile's aggregate
     int32_t dbg;              // bring-up (DBG build): bit0 skip MMAs, bit1 skip scan math, bit2 skip stores, bit3 print waits, bit4 skip correction
@@ -200,13 +208,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
     auto D_FULL = [&](int b) { return bar0 + 8u * (3 * NSTAGE + 2 * NACC + b); };
     auto D_EMPTY = [&](int b) { return bar0 + 8u * (3 * NSTAGE + 3 * NACC + b); };
     auto S_READY = [&](int b) { return bar0 + 8u * (3 * NSTAGE + 4 * NACC + b); };
-    auto S_EMPTY = [&](int b) { return bar0 + 8u * (3 * NSTAGE + 5 * NACC + b); };
+    auto SOP_EMPTY = [&](int b) { return bar0 + 8u * (3 * NSTAGE + 5 * NACC + b); };
     auto Z_READY = [&](int b) { return bar0 + 8u * (3 * NSTAGE + 6 * NACC + b); };
     auto ESM_READY = [&](int b) { return bar0 + 8u * (3 * NSTAGE + 7 * NACC + b); };
     auto ESM_EMPTY = [&](int b) { return bar0 + 8u * (3 * NSTAGE + 8 * NACC + b); };
+    auto Z_EMPTY = [&](int b) { return bar0 + 8u * (3 * NSTAGE + 9 * NACC + b); };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + SM_MISC);
     float *wmax = reinterpret_cast<float *>(sm + SM_MISC + 16);
     int *tile_e = reinterpret_cast<int *>(sm + SM_MISC + 32);
+    float *tile_m = reinterpret_cast<float *>(sm + SM_MISC + 32 + 4 * E_RING);
     double *smat = reinterpret_cast<double *>(sm + SM_SMAT);
     float *fold = reinterpret_cast<float *>(sm + SM_FOLD);
     float *esm = reinterpret_cast<float *>(sm + SM_ESM);
@@ -225,13 +235,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
             mbar_init(D_FULL(b), 1);
             mbar_init(D_EMPTY(b), N_EPI_WARPS);
             mbar_init(S_READY(b), 1);
-            mbar_init(S_EMPTY(b), N_EPI_WARPS);
+            mbar_init(SOP_EMPTY(b), 1);
+            mbar_init(Z_EMPTY(b), 1);
             mbar_init(Z_READY(b), 1);
             mbar_init(ESM_READY(b), 1);
             mbar_init(ESM_EMPTY(b), 1);
         }
         fence_barrier_init();
     }
+    if (tid < E_RING) tile_m[tid] = 0.f;
+    // the correction operand rows hold 32 of 64 fp16: clear the rest once (0 * garbage could be NaN)
+    for (int i = tid; i < 2 * SOP_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4 *>(sm + SM_SOP)[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < NSMAT * ND * ND; i += NTHREADS) smat[i] = a.smat[i];
     for (int i = tid; i < NFOLD * FOLD_PITCH; i += NTHREADS) fold[i] = a.fold[i];
     if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -316,10 +330,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
             float bm = 0.f;
 #pragma unroll
             for (int w = 0; w < N_CVT_WARPS; ++w) bm = fmaxf(bm, wmax[w]);
-            int ex = 14;
-            if (bm > 0.f && bm < 3.0e38f) (void)frexpf(bm, &ex);
-            const int e = max(-110, min(110, 14 - ex));
+            // block scale from the largest |x| of the last `win` tiles (the cascade's memory): the chunk start states
+            // of this tile are then bounded by the plan-time gain times that maximum, so they fit the fp16 operand of
+            // the correction GEMM whatever the signal does
+            float wm = bm;
+#pragma unroll 1
+            for (int j = 1; j < a.win; ++j)
+                if (it - j >= 0) wm = fmaxf(wm, tile_m[(it - j) % E_RING]);
+            if (blockIdx.x == 0 && a.zi != nullptr && it < a.win) {
+                for (int k = 0; k < a.d_real; ++k) wm = fmaxf(wm, fabsf(a.zi[k]) * a.ginv[k]);
+            }
+            int ex = a.xexp;
+            if (wm > 0.f && wm < 3.0e38f) (void)frexpf(wm, &ex);
+            const int e = max(-100, min(100, a.xexp - ex));
             const float sx = ldexpf(1.0f, e);
+            if (ct == 0) tile_m[it % E_RING] = bm;
 #pragma unroll
             for (int i = 0; i < G_PER_THREAD; ++i) {
                 const int c = c_first + 4 * i;                                   // chunk = row of the operand region
@@ -490,8 +515,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
                     Mt = MKS + (st - 1) * mstride;
                     active = lane >= off;
                 } else {
-                    // the chain warp has consumed the previous aggregate / start states of this buffer
-                    STC_WAIT(S_EMPTY(b), pb ^ 1u, 6);
+                    // the chain warp has consumed the previous aggregate / zero-state start states of this buffer
+                    STC_WAIT(Z_EMPTY(b), pb ^ 1u, 6);
 #pragma unroll
                     for (int k = 0; k < ND; ++k) {
                         o[k] = __shfl_up_sync(0xffffffffu, q[k], 1);
@@ -539,67 +564,76 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
         const float *Ph = fold + (lane >> 2) * FOLD_PITCH, *Qm = fold + (8 + (lane & 3)) * FOLD_PITCH;
         const float *F128 = fold + 12 * FOLD_PITCH;
         const double *MAT = smat + 6 * ND * ND;            // A^8192
-        // epilogue warp 0 also issues the output MMAs of tile it+2 as soon as tile it has left its accumulator: zero-state
-        // outputs, rows = the 128 positions of a chunk, K = the chunk's 128 samples (even row then odd row); three
-        // partial products, smallest first: T_hi x_lo, T_lo x_hi, T_hi x_hi
-        auto issue_y = [&](int yit) {
-            const int s = yit % NSTAGE;
-            const int yb = yit & 1;
-            const uint32_t st = base + s * STAGE_BYTES;
-            const uint32_t acc = tmem_base + ACC_COL0 + yb * ACC_STRIDE;
-            const uint64_t xe_hi = make_desc_sw128(st + 0 * REGION), xe_lo = make_desc_sw128(st + 1 * REGION);
-            const uint64_t xo_hi = make_desc_sw128(st + 2 * REGION), xo_lo = make_desc_sw128(st + 3 * REGION);
-            STC_WAIT(D_EMPTY(yb), ((uint32_t)(yit >> 1) & 1u) ^ 1u, 4);
-            STC_WAIT(A_FULL(s), (uint32_t)(yit / NSTAGE) & 1u, 2);
-            tc_fence_after();
-            if (elect_one()) {
-                if (!(DBG && (a.dbg & 1))) {
-#pragma unroll
-                    for (int sl = 0; sl < 8; ++sl)
-                        umma_f16_ts(acc, tmem_base + COL_THI + sl * 8, (sl < 4 ? xe_lo : xo_lo) + (uint64_t)(2 * (sl & 3)), kIdesc, sl > 0);
-#pragma unroll
-                    for (int sl = 0; sl < 8; ++sl)
-                        umma_f16_ts(acc, tmem_base + COL_TLO + sl * 8, (sl < 4 ? xe_hi : xo_hi) + (uint64_t)(2 * (sl & 3)), kIdesc, 1);
-#pragma unroll
-                    for (int sl = 0; sl < 8; ++sl)
-                        umma_f16_ts(acc, tmem_base + COL_THI + sl * 8, (sl < 4 ? xe_hi : xo_hi) + (uint64_t)(2 * (sl & 3)), kIdesc, 1);
-                }
-                umma_commit(D_FULL(yb));
-                umma_commit(A_EMPTY(s));
-            }
-            __syncwarp();
-        };
-        const int n_it = (int)(t_end - t_begin);
-        for (int it = -2; it < n_it; ++it) {
-            if (it < 0) {
-                if (warp == 0 && it + 2 < n_it) issue_y(it + 2);
-                continue;
-            }
-            const int64_t tile = t_begin + it;
+        int it = 0;
+        for (int64_t tile = t_begin; tile < t_end; ++tile, ++it) {
             const int b = it & 1;
             const uint32_t pb = (uint32_t)(it >> 1) & 1u;
-            float sf[ND], u[ND], h0[ND], h1[ND];
+            // fold: h0 = A^(256 m) A^(1024 h) s_in, h1 = A^128 h0 -- one matvec body, three passes (code footprint)
+            float h0[ND], h1[ND];
 #pragma unroll
-            for (int k = 0; k < ND; ++k) sf[k] = (float)s_in[k];
-            mv_f32<ND>(u, Ph, sf);
-            mv_f32<ND>(h0, Qm, u);                         // A^(256 l) s_in : correction of chunk 2l
-            mv_f32<ND>(h1, F128, h0);                      // chunk 2l+1
+            for (int k = 0; k < ND; ++k) h1[k] = (float)s_in[k];
+#pragma unroll 1
+            for (int pass = 0; pass < 3; ++pass) {
+                const float *Mt = (pass == 0) ? Ph : (pass == 1 ? Qm : F128);
+#pragma unroll
+                for (int k = 0; k < ND; ++k) { h0[k] = h1[k]; }
+                mv_f32<ND>(h1, Mt, h0);
+            }
+            // now h1 = chunk 2l+1's share, h0 = chunk 2l's share (the input of the last pass)
             STC_WAIT(Z_READY(b), pb, 8);
             double nxt[ND];
 #pragma unroll
             for (int k = 0; k < ND; ++k) nxt[k] = aggsm[b * 16 + k];
             if (!a.at_zero) mv_acc<ND>(nxt, MAT, s_in);
-            float *d0 = s0sm + (b * NCHUNK + 2 * lane) * EP, *d1 = d0 + EP;
+            const float *d0 = s0sm + (b * NCHUNK + 2 * lane) * EP, *d1 = d0 + EP;
 #pragma unroll
             for (int k = 0; k < ND; k += 4) {
-                float4 z0 = *reinterpret_cast<const float4 *>(d0 + k), z1 = *reinterpret_cast<const float4 *>(d1 + k);
-                z0.x += h0[k]; z0.y += h0[k + 1]; z0.z += h0[k + 2]; z0.w += h0[k + 3];
-                z1.x += h1[k]; z1.y += h1[k + 1]; z1.z += h1[k + 2]; z1.w += h1[k + 3];
-                *reinterpret_cast<float4 *>(d0 + k) = z0;
-                *reinterpret_cast<float4 *>(d1 + k) = z1;
-                h0[k] = z0.x; h0[k + 1] = z0.y; h0[k + 2] = z0.z; h0[k + 3] = z0.w;     // keep the start states (final state)
-                h1[k] = z1.x; h1[k + 1] = z1.y; h1[k + 2] = z1.z; h1[k + 3] = z1.w;
+                const float4 z0 = *reinterpret_cast<const float4 *>(d0 + k), z1 = *reinterpret_cast<const float4 *>(d1 + k);
+                h0[k] += z0.x; h0[k + 1] += z0.y; h0[k + 2] += z0.z; h0[k + 3] += z0.w;     // true start state of chunk 2l
+                h1[k] += z1.x; h1[k + 1] += z1.y; h1[k + 2] += z1.z; h1[k + 3] += z1.w;     //                     chunk 2l+1
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(Z_EMPTY(b));
+            // the two chunk rows of the correction operand: fp16 hi (k 0..15) and residual (k 16..31) of s_d * sfac[d] * 2^e_x
+            STC_WAIT(SOP_EMPTY(b), pb ^ 1u, 7);
+            {
+                const float px = ldexpf(1.0f, tile_e[it % E_RING]);
+                unsigned char *sop = sm + SM_SOP + b * SOP_BYTES;
+                float hv[ND];
+#pragma unroll
+                for (int k = 0; k < ND; ++k) hv[k] = h0[k];
+#pragma unroll 1
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int c = 2 * lane + hh;
+                    if (hh) {
+#pragma unroll
+                        for (int k = 0; k < ND; ++k) hv[k] = h1[k];
+                    }
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int k = 0; k < 16; k += 2) {
+                        float v0 = 0.f, v1 = 0.f;
+                        if (k < ND) {
+                            v0 = hv[k] * (a.sfac[k] * px);
+                            v1 = hv[k + 1] * (a.sfac[k + 1] * px);
+                            v0 = fminf(fmaxf(v0, -60000.f), 60000.f);          // never reached inside the plan's gain bound
+                            v1 = fminf(fmaxf(v1, -60000.f), 60000.f);
+                        }
+                        const __half2 h = __floats2half2_rn(v0, v1);
+                        const float2 f = __half22float2(h);
+                        const __half2 l = __floats2half2_rn(v0 - f.x, v1 - f.y);
+                        hi[k >> 1] = *reinterpret_cast<const uint32_t *>(&h);
+                        lo[k >> 1] = *reinterpret_cast<const uint32_t *>(&l);
+                    }
+                    unsigned char *row = sop + c * 128;
+                    const int sw = c & 7;
+                    *reinterpret_cast<uint4 *>(row + ((0 ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4 *>(row + ((1 ^ sw) << 4)) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                    *reinterpret_cast<uint4 *>(row + ((2 ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    *reinterpret_cast<uint4 *>(row + ((3 ^ sw) << 4)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                }
+            }
+            fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(S_READY(b));
 
@@ -640,9 +674,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
         // consecutive samples (128 bytes)
         const int qd = warp & 3, half = warp >> 2;
         const int rho = qd * 32 + lane;
-        float ot[ND];
-#pragma unroll
-        for (int k = 0; k < ND; ++k) ot[k] = a.otab[rho * 16 + k];
         const uint32_t lane_sel = (uint32_t)(qd * 32) << 16;
         const int colbase = half * 32;
         // epilogue warp 0 also issues the output MMAs of tile it+2 as soon as tile it has left its accumulator: zero-state
@@ -670,13 +701,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
                     for (int sl = 0; sl < 8; ++sl)
                         umma_f16_ts(acc, tmem_base + COL_THI + sl * 8, (sl < 4 ? xe_hi : xo_hi) + (uint64_t)(2 * (sl & 3)), kIdesc, 1);
                 }
-                umma_commit(D_FULL(yb));
                 umma_commit(A_EMPTY(s));
             }
             __syncwarp();
         };
+        // ... and the correction  Y += O S  of a tile once the chain warp has written its chunk start states; the commit
+        // after it covers the tile's output MMAs as well (same issuing thread, same accumulator)
+        auto issue_corr = [&](int cit) {
+            const int cb = cit & 1;
+            const uint32_t acc = tmem_base + ACC_COL0 + cb * ACC_STRIDE;
+            const uint64_t sd = make_desc_sw128(base + SM_SOP + cb * SOP_BYTES);
+            STC_WAIT(S_READY(cb), (uint32_t)(cit >> 1) & 1u, 8);
+            tc_fence_after();
+            if (elect_one()) {
+                if (!(DBG && (a.dbg & 1))) {
+                    umma_f16_ts(acc, tmem_base + COL_OLO, sd, kIdesc, 1);                       // O_lo S_hi
+                    umma_f16_ts(acc, tmem_base + COL_OHI, sd + 2, kIdesc, 1);                   // O_hi S_lo
+                    umma_f16_ts(acc, tmem_base + COL_OHI, sd, kIdesc, 1);                       // O_hi S_hi
+                }
+                umma_commit(D_FULL(cb));
+                umma_commit(SOP_EMPTY(cb));
+            }
+            __syncwarp();
+        };
         const int n_it = (int)(t_end - t_begin);
+        int corr_next = 0;                                // next tile whose correction has not been issued (warp 0)
         for (int it = -2; it < n_it; ++it) {
+            if (warp == 0) {
+                // keep the tensor pipe's queue in the order the data becomes ready: a correction that can go now goes
+                // before the next output MMAs (it is three MMAs and unblocks all eight epilogue warps)
+                if (it >= 0 && corr_next == it) { issue_corr(it); ++corr_next; }
+            }
             if (it < 0) {
                 if (warp == 0 && it + 2 < n_it) issue_y(it + 2);
                 continue;
@@ -693,7 +748,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
             // samples of this tile that exist and are to be stored (0 for warm-up tiles)
             int limit = 0;
             if (tile >= t_own && !(DBG && (a.dbg & 4))) limit = (int)((a.n_rate - tile0 < TILE) ? a.n_rate - tile0 : TILE);
-            const float *s0 = s0sm + (b * NCHUNK + colbase) * EP;
             int p = colbase * LC + rho;                    // position inside the tile
             float *yp = a.y + tile0 + p;
             // decimating stores keep positions g with g % M == 0: (m, r) = (g / M, g % M) walked without divisions
@@ -706,7 +760,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
                 step_m = LC / a.M;
                 step_r = LC - step_m * a.M;
             }
-            STC_WAIT(S_READY(b), pb, 8);
             // rolled over groups of 8 chunks: the loop body stays resident in the instruction cache
 #pragma unroll 1
             for (int c0 = 0; c0 < 32; c0 += 8) {
@@ -718,24 +771,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
                     __syncwarp();
                     if (lane == 0) mbar_arrive(D_EMPTY(b));
                 }
-                // correction y += (C A^rho) . S_c : state index outer, chunk inner -> 8 independent FMA chains and the
-                // shared-memory loads (all lanes read the same address: broadcast) issued back to back
                 float acc[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) acc[c] = __uint_as_float(dv[c]) * inv;
-                if (!(DBG && (a.dbg & 16))) {
-#pragma unroll
-                    for (int k = 0; k < ND; k += 4) {
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            const float4 sv = *reinterpret_cast<const float4 *>(s0 + c * EP + k);
-                            acc[c] = fmaf(ot[k], sv.x, acc[c]);
-                            acc[c] = fmaf(ot[k + 1], sv.y, acc[c]);
-                            acc[c] = fmaf(ot[k + 2], sv.z, acc[c]);
-                            acc[c] = fmaf(ot[k + 3], sv.w, acc[c]);
-                        }
-                    }
-                }
                 if (a.M == 1) {
 #pragma unroll
                     for (int c = 0; c < 8; ++c)
@@ -749,14 +787,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
                         if (r >= a.M) { r -= a.M; ++m; }
                     }
                 }
-                s0 += 8 * EP;
                 p += 8 * LC;
                 yp += 8 * LC;
             }
             __syncwarp();
             if (DBG) ph_b += clock64() - tp0;
-            if (lane == 0) mbar_arrive(S_EMPTY(b));
-            if (warp == 0 && it + 2 < n_it) issue_y(it + 2);
+            if (warp == 0) {
+                // tile it+1's correction first if its states are already there, then the output MMAs of tile it+2
+                if (it + 1 < n_it && corr_next == it + 1 && mbar_test(S_READY((it + 1) & 1), (uint32_t)((it + 1) >> 1) & 1u)) {
+                    issue_corr(it + 1);
+                    ++corr_next;
+                }
+                if (it + 2 < n_it) issue_y(it + 2);
+            }
         }
     }
     if (DBG && (a.dbg & 8) && blockIdx.x == 1 && lane == 0)
@@ -869,11 +912,11 @@ int stc_build(const double (*coef)[5], int nsec, int nsec_real, StcTables *t)
     int warm = 1;
     {
         Mat Q = AT;                                        // A^8192
-        while (maxabs(Q) * ND > 1e-13 && warm <= 64) {
+        while (maxabs(Q) * ND > 1e-13 && warm < MAXWIN) {
             mm(Q, AT, Q, ND);
             ++warm;
         }
-        if (warm > 64) return B200DSP_OK;                  // decays too slowly: scan kernels
+        if (maxabs(Q) * ND > 1e-13) return B200DSP_OK;     // decays too slowly: scan kernels
     }
     // Kogge-Stone levels that matter: A^(256 * 2^j) below float64 resolution of the state contributes nothing
     int nlev = 0;
@@ -922,10 +965,45 @@ int stc_build(const double (*coef)[5], int nsec, int nsec_real, StcTables *t)
             for (int k = 0; k < LC; ++k) m = fmax(m, fabs(w[k][dd]));
         e_row[dd] = scale_exp(m);
     }
+    // Correction operand scales.  g_d = sum_k |(A^k B)_d| bounds |s_d| <= g_d max|x| (over the cascade's memory =
+    // the window the block scale looks at), so with f_d = ceil(log2 g_d) the operand s_d 2^-f_d never exceeds the
+    // window maximum; the rows of O carry 2^f_d back.  e_o puts the largest |O_d 2^f_d| just under 2^14.
+    int f_exp[16];
+    {
+        std::vector<double> g(ND, 0.0), wk = Bv, wn(ND);
+        const long steps = (long)warm * STC_TILE;
+        for (long k = 0; k < steps; ++k) {
+            for (int i = 0; i < ND; ++i) g[i] += fabs(wk[i]);
+            for (int i = 0; i < ND; ++i) {
+                double acc = 0.0;
+                for (int j = 0; j < ND; ++j) acc += A[i * ND + j] * wk[j];
+                wn[i] = acc;
+            }
+            wk.swap(wn);
+        }
+        for (int dd = 0; dd < 16; ++dd) {
+            int ex = 0;
+            if (dd < ND && g[dd] > 0.0) (void)frexp(g[dd], &ex);     // g < 2^ex
+            f_exp[dd] = ex;
+        }
+    }
+    double omax = 0.0;
+    for (int n = 0; n < LC; ++n)
+        for (int dd = 0; dd < ND; ++dd) omax = fmax(omax, fabs(ldexp(orow[n][dd], f_exp[dd])));
+    int e_o = 0;
+    if (omax > 0.0) {
+        int ex = 0;
+        (void)frexp(omax, &ex);
+        e_o = 14 - ex;
+    }
+    // |s_d| sfac_d 2^e_x <= max|x| 2^e_x 2^(e_t - e_o) < 2^(xexp + e_t - e_o) must stay below 2^15 (one bit spare)
+    int xexp = 14 - (e_t - e_o);
+    if (xexp > 12) xexp = 12;
+    if (xexp < 2) return B200DSP_OK;                       // states too large against the outputs for the fp16 operand
     // TMEM image, one row per lane (192 columns = 384 fp16):
     //   T_hi | T_lo : lane rho = position inside the chunk, k = sample of the chunk: h[rho - k] (k <= rho), fp16 hi / residual
     //   Ka | Kb     : lanes 0-15 = fp16 hi of state row d = lane, lanes 16-31 = its residual (summed by the scan warp)
-    std::vector<__half> img((size_t)128 * 2 * A_COLS);
+    std::vector<__half> img((size_t)128 * 2 * A_COLS, __float2half_rn(0.f));
     for (int rho = 0; rho < 128; ++rho) {
         __half *row = img.data() + (size_t)rho * 2 * A_COLS;
         for (int kk = 0; kk < LC; ++kk) {
@@ -933,6 +1011,12 @@ int stc_build(const double (*coef)[5], int nsec, int nsec_real, StcTables *t)
             const __half hi = __float2half_rn((float)v);
             row[2 * COL_THI + kk] = hi;
             row[2 * COL_TLO + kk] = __float2half_rn((float)(v - (double)__half2float(hi)));
+        }
+        for (int k = 0; k < 16; ++k) {
+            const double v = (k < ND) ? ldexp(orow[rho][k], f_exp[k] + e_o) : 0.0;
+            const __half hi = __float2half_rn((float)v);
+            row[2 * COL_OHI + k] = hi;
+            row[2 * COL_OLO + k] = __float2half_rn((float)(v - (double)__half2float(hi)));
         }
         const int dd = rho & 15;
         const bool lo = (rho & 16) != 0;
@@ -945,9 +1029,7 @@ int stc_build(const double (*coef)[5], int nsec, int nsec_real, StcTables *t)
                 row[2 * (ab == 0 ? COL_KA : COL_KB) + kk] = lo ? lw : hi;
             }
     }
-    std::vector<float> otab((size_t)LC * 16, 0.f), rowinv(16, 1.f);
-    for (int n = 0; n < LC; ++n)
-        for (int dd = 0; dd < ND; ++dd) otab[(size_t)n * 16 + dd] = (float)orow[n][dd];
+    std::vector<float> rowinv(16, 1.f);
     for (int dd = 0; dd < 16; ++dd) rowinv[dd] = (float)ldexp(1.0, -e_row[dd]);
 
     t->nd = ND;
@@ -956,17 +1038,20 @@ int stc_build(const double (*coef)[5], int nsec, int nsec_real, StcTables *t)
     t->warm_tiles = warm;
     t->nlev = nlev;
     t->at_zero = at_zero;
+    t->xexp = xexp;
+    for (int dd = 0; dd < 16; ++dd) {
+        t->sfac[dd] = (float)ldexp(1.0, e_t - e_o - f_exp[dd]);
+        t->ginv[dd] = (float)ldexp(1.0, -f_exp[dd]);
+    }
     memset(t->coef, 0, sizeof(t->coef));
     for (int s = 0; s < nsec; ++s)
         for (int q = 0; q < 5; ++q) t->coef[s][q] = coef[s][q];
     cudaError_t e = cudaMalloc(&t->amat, img.size() * sizeof(__half));
-    if (e == cudaSuccess) e = cudaMalloc(&t->otab, otab.size() * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&t->smat, smat.size() * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&t->rowinv, rowinv.size() * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&t->fold, foldm.size() * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpy(t->fold, foldm.data(), foldm.size() * sizeof(float), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(t->amat, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(t->otab, otab.data(), otab.size() * sizeof(float), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(t->smat, smat.data(), smat.size() * sizeof(double), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(t->rowinv, rowinv.data(), rowinv.size() * sizeof(float), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaStreamSynchronize(0);
@@ -982,13 +1067,11 @@ int stc_build(const double (*coef)[5], int nsec, int nsec_real, StcTables *t)
 void stc_free(StcTables *t)
 {
     cudaFree(t->amat);
-    cudaFree(t->otab);
     cudaFree(t->smat);
     cudaFree(t->rowinv);
     cudaFree(t->fold);
     t->fold = nullptr;
     t->amat = nullptr;
-    t->otab = nullptr;
     t->smat = nullptr;
     t->rowinv = nullptr;
     t->ok = false;
@@ -1027,11 +1110,14 @@ int launch_sos_tc(const StcTables &t, const float *x, float *y, int64_t n_in, in
     a.x = x;
     a.y = y;
     a.amat = static_cast<const uint4 *>(t.amat);
-    a.otab = t.otab;
     a.smat = t.smat;
     a.fold = t.fold;
     a.nlev = t.nlev;
     a.at_zero = t.at_zero;
+    a.xexp = t.xexp;
+    a.win = t.warm_tiles + 1 > 8 ? 8 : t.warm_tiles + 1;
+    memcpy(a.sfac, t.sfac, sizeof(a.sfac));
+    memcpy(a.ginv, t.ginv, sizeof(a.ginv));
     a.rowinv = t.rowinv;
     a.zi = zi;
     a.zf = zf;

@@ -16,9 +16,11 @@ struct StcTables {
     int warm_tiles = 0;                  // tiles a block runs ahead of its first output (state warm-up)
     int nlev = 0;                        // scan levels whose matrix A^(256 * 2^j) is above float64 resolution
     int at_zero = 0;                     // A^8192 negligible
+    int xexp = 12;                       // block scale: window max of |x| -> [2^(xexp-1), 2^xexp)
+    float sfac[16];                      // correction operand scale per state (x 2^e_x at run time)
+    float ginv[16];                      // 2^-f_d: |s_d| ginv[d] <= max |x| over the cascade's memory
     double coef[STC_MAXSEC][5];          // b0 b1 b2 -a1 -a2 (final-state tail recurrence)
-    void *amat = nullptr;                // [128 lanes][384 fp16]  (T_hi | T_lo | Ka | Kb), TMEM image
-    float *otab = nullptr;               // [128][16]     zero-input response rows  C A^n
+    void *amat = nullptr;                // [128 lanes][416 fp16]  (T_hi | T_lo | Ka | Kb), TMEM image
     double *smat = nullptr;              // [6][nd*nd]    A^128, A^256, ... A^4096, column-major
     float *rowinv = nullptr;             // [16]          2^-e_d of the carry rows
     float *fold = nullptr;               // [13][260]     float32 A^(1024 h) | A^(256 m) | A^128, column-major

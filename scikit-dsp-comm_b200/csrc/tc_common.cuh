@@ -45,6 +45,12 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     return done != 0;
 }
+// the failure path lives out of line: ~25 wait sites per kernel would otherwise each carry a printf call sequence
+// (instruction-cache footprint of the warp-specialised kernels)
+static __device__ __noinline__ void mbar_timeout(int who) {
+    printf("b200dsp tensor-core kernel: mbarrier timeout (role %d, block %d)\n", who, (int)blockIdx.x);
+    __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int who) {
     uint64_t t0 = 0;
     for (uint32_t spin = 1;; ++spin) {
@@ -55,8 +61,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int who
             else if (t - t0 > 20000000000ull) break;
         }
     }
-    printf("b200dsp tensor-core kernel: mbarrier timeout (role %d, block %d)\n", who, (int)blockIdx.x);
-    __trap();
+    mbar_timeout(who);
 }
 // one elected lane of a converged warp (lets ptxas emit UTCHMMA / UBLKCP without a lane loop)
 __device__ __forceinline__ bool elect_one() {
