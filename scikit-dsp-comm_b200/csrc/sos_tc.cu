@@ -43,8 +43,9 @@ constexpr int LC = 128;                       // samples per chunk
 constexpr int TILE = NCHUNK * LC;             // 8192
 static_assert(TILE == STC_TILE, "tile size");
 constexpr int REGION = NCHUNK * BK * 2;       // one fp16 operand region: 64 rows x 128 B
-constexpr int STAGE_BYTES = 4 * REGION;       // (even,odd) x (hi,lo) = the raw fp32 tile, converted in place
-constexpr int NSTAGE = 4;
+constexpr int STAGE_BYTES = 4 * REGION;       // (even,odd) x (hi,lo); the raw fp32 tile has the same size
+constexpr int NSTAGE = 3;                     // operand ring (fp16 regions, read by the MMAs)
+constexpr int NRAW = 2;                       // raw ring (fp32 tiles written by bulk TMA, read by the converters)
 constexpr int NACC = 2;
 // TMEM columns: T_hi (128 rows x 128 k -> 64 columns) | T_lo (64) | Ka (32) | Kb (32) | O_hi (8) | O_lo (8) | accumulators
 constexpr int COL_THI = 0, COL_TLO = 64, COL_KA = 128, COL_KB = 160, COL_OHI = 192, COL_OLO = 200;
@@ -70,14 +71,15 @@ constexpr int MAXWIN = 8;                     // tiles of input history that bou
 constexpr int SOP_BYTES = NCHUNK * 128;       // chunk start states as an MMA operand: 64 rows x (16 hi | 16 lo | pad) fp16
 
 // shared memory map (offsets from the 1024-aligned base)
-constexpr int SM_SOP = NSTAGE * STAGE_BYTES;                  // [2][SOP_BYTES]           K-major SWIZZLE_128B, 1024-aligned
+constexpr int SM_RAW = NSTAGE * STAGE_BYTES;                  // [NRAW][STAGE_BYTES]      raw fp32 tiles
+constexpr int SM_SOP = SM_RAW + NRAW * STAGE_BYTES;           // [2][SOP_BYTES]           K-major SWIZZLE_128B, 1024-aligned
 constexpr int SM_SMAT = SM_SOP + 2 * SOP_BYTES;               // double [7][16*16]
 constexpr int SM_FOLD = SM_SMAT + NSMAT * 256 * 8;            // float [18][FOLD_PITCH]
-constexpr int SM_ESM = SM_FOLD + NFOLD * FOLD_PITCH * 4;      // float [2][64][EP]        carries (warp 8 -> scan warp b)
-constexpr int SM_S0 = SM_ESM + 2 * NCHUNK * EP * 4;           // float [2][64][EP]        zero-state chunk start states (scan -> chain)
-constexpr int SM_AGG = SM_S0 + 2 * NCHUNK * EP * 4;           // double [2][16]           zero-state end state of a tile
+constexpr int SM_ESM = SM_FOLD + NFOLD * FOLD_PITCH * 4;      // float [2][64][EP]   carries (warp 8 -> scan warp b), overwritten in
+                                                              //                     place by the zero-state start states (-> chain)
+constexpr int SM_AGG = SM_ESM + 2 * NCHUNK * EP * 4;          // double [2][16]           zero-state end state of a tile
 constexpr int SM_BAR = SM_AGG + 2 * 16 * 8;
-constexpr int NBAR = 3 * NSTAGE + 10 * NACC;
+constexpr int NBAR = 2 * NRAW + 2 * NSTAGE + 9 * NACC;
 constexpr int SM_MISC = SM_BAR + NBAR * 8;                    // tmem slot, wmax[4], tile_e[16], tile_m[16]
 constexpr int SMEM_TOTAL = SM_MISC + 256 + 1024;
 static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
@@ -200,32 +202,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     const uint32_t bar0 = base + SM_BAR;
-    auto RAW_FULL = [&](int s) { return bar0 + 8u * s; };
-    auto A_FULL = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
-    auto A_EMPTY = [&](int s) { return bar0 + 8u * (2 * NSTAGE + s); };
-    auto E_FULL = [&](int b) { return bar0 + 8u * (3 * NSTAGE + b); };
-    auto E_EMPTY = [&](int b) { return bar0 + 8u * (3 * NSTAGE + NACC + b); };
-    auto D_FULL = [&](int b) { return bar0 + 8u * (3 * NSTAGE + 2 * NACC + b); };
-    auto D_EMPTY = [&](int b) { return bar0 + 8u * (3 * NSTAGE + 3 * NACC + b); };
-    auto S_READY = [&](int b) { return bar0 + 8u * (3 * NSTAGE + 4 * NACC + b); };
-    auto SOP_EMPTY = [&](int b) { return bar0 + 8u * (3 * NSTAGE + 5 * NACC + b); };
-    auto Z_READY = [&](int b) { return bar0 + 8u * (3 * NSTAGE + 6 * NACC + b); };
-    auto ESM_READY = [&](int b) { return bar0 + 8u * (3 * NSTAGE + 7 * NACC + b); };
-    auto ESM_EMPTY = [&](int b) { return bar0 + 8u * (3 * NSTAGE + 8 * NACC + b); };
-    auto Z_EMPTY = [&](int b) { return bar0 + 8u * (3 * NSTAGE + 9 * NACC + b); };
+    constexpr int B0 = 2 * NRAW + 2 * NSTAGE;
+    auto RAW_FULL = [&](int r) { return bar0 + 8u * r; };
+    auto RAW_EMPTY = [&](int r) { return bar0 + 8u * (NRAW + r); };
+    auto A_FULL = [&](int s) { return bar0 + 8u * (2 * NRAW + s); };
+    auto A_EMPTY = [&](int s) { return bar0 + 8u * (2 * NRAW + NSTAGE + s); };
+    auto E_FULL = [&](int b) { return bar0 + 8u * (B0 + b); };
+    auto E_EMPTY = [&](int b) { return bar0 + 8u * (B0 + NACC + b); };
+    auto D_FULL = [&](int b) { return bar0 + 8u * (B0 + 2 * NACC + b); };
+    auto D_EMPTY = [&](int b) { return bar0 + 8u * (B0 + 3 * NACC + b); };
+    auto S_READY = [&](int b) { return bar0 + 8u * (B0 + 4 * NACC + b); };
+    auto SOP_EMPTY = [&](int b) { return bar0 + 8u * (B0 + 5 * NACC + b); };
+    auto Z_READY = [&](int b) { return bar0 + 8u * (B0 + 6 * NACC + b); };
+    auto ESM_READY = [&](int b) { return bar0 + 8u * (B0 + 7 * NACC + b); };
+    auto ESM_EMPTY = [&](int b) { return bar0 + 8u * (B0 + 8 * NACC + b); };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + SM_MISC);
     float *wmax = reinterpret_cast<float *>(sm + SM_MISC + 16);
-    int *tile_e = reinterpret_cast<int *>(sm + SM_MISC + 32);
-    float *tile_m = reinterpret_cast<float *>(sm + SM_MISC + 32 + 4 * E_RING);
+    int *tile_e = reinterpret_cast<int *>(sm + SM_MISC + 48);                    // wmax: [2][4] floats
+    float *tile_m = reinterpret_cast<float *>(sm + SM_MISC + 48 + 4 * E_RING);
     double *smat = reinterpret_cast<double *>(sm + SM_SMAT);
     float *fold = reinterpret_cast<float *>(sm + SM_FOLD);
     float *esm = reinterpret_cast<float *>(sm + SM_ESM);
-    float *s0sm = reinterpret_cast<float *>(sm + SM_S0);
     double *aggsm = reinterpret_cast<double *>(sm + SM_AGG);
 
     if (tid == 0) {
+        for (int r = 0; r < NRAW; ++r) {
+            mbar_init(RAW_FULL(r), 1);
+            mbar_init(RAW_EMPTY(r), N_CVT_WARPS);
+        }
         for (int s = 0; s < NSTAGE; ++s) {
-            mbar_init(RAW_FULL(s), 1);
             mbar_init(A_FULL(s), N_CVT_WARPS);
             mbar_init(A_EMPTY(s), 2);                      // carry MMAs (warp 8) + output MMAs (warp 0) have read the stage
         }
@@ -236,7 +241,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
             mbar_init(D_EMPTY(b), N_EPI_WARPS);
             mbar_init(S_READY(b), 1);
             mbar_init(SOP_EMPTY(b), 1);
-            mbar_init(Z_EMPTY(b), 1);
             mbar_init(Z_READY(b), 1);
             mbar_init(ESM_READY(b), 1);
             mbar_init(ESM_EMPTY(b), 1);
@@ -287,13 +291,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
         const int parity = (ct >> 4) & 1, c_first = ct >> 5, colb = (ct & 15) >> 1, sub = (ct & 1) * 8;
         int it = 0;
         for (int64_t tile = t_begin; tile < t_end; ++tile, ++it) {
-            const int s = it % NSTAGE;
-            const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
+            const int r = it % NRAW, s = it % NSTAGE;
+            const unsigned char *raw = sm + SM_RAW + r * STAGE_BYTES;
             unsigned char *st = sm + s * STAGE_BYTES;
-            STC_WAIT(RAW_FULL(s), ph, 1);
+            STC_WAIT(RAW_FULL(r), (uint32_t)(it / NRAW) & 1u, 1);
             if (!tile_is_bulk(a, tile)) {
                 // edge / unaligned / zero-stuffed tile: the converters fetch it themselves into the raw layout
-                float *rawf = reinterpret_cast<float *>(st);
+                float *rawf = reinterpret_cast<float *>(sm + SM_RAW + r * STAGE_BYTES);
                 const int64_t g0 = tile * (int64_t)TILE;
                 if (a.L == 1) {
 #pragma unroll 1
@@ -314,22 +318,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(N_CVT));
             }
-            float4 raw4[G_PER_THREAD];
+            // pass 1 (rolled): tile maximum.  The raw tile stays in shared memory and is read again by pass 2 -- both
+            // passes are short loops that stay in the instruction cache
             float m = 0.f;
-#pragma unroll
+#pragma unroll 4
             for (int i = 0; i < G_PER_THREAD; ++i) {
-                const float4 v = reinterpret_cast<const float4 *>(st)[ct + i * N_CVT];
-                raw4[i] = v;
+                const float4 v = reinterpret_cast<const float4 *>(raw)[ct + i * N_CVT];
                 m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            // wmax is double buffered by tile parity: one named barrier per tile is enough
+            if (lane == 0) wmax[(it & 1) * N_CVT_WARPS + cw] = m;
             asm volatile("bar.sync 1, %0;" ::"n"(N_CVT));
-            if (lane == 0) wmax[cw] = m;
-            asm volatile("bar.sync 1, %0;" ::"n"(N_CVT));        // all raw samples are in registers
             float bm = 0.f;
 #pragma unroll
-            for (int w = 0; w < N_CVT_WARPS; ++w) bm = fmaxf(bm, wmax[w]);
+            for (int w = 0; w < N_CVT_WARPS; ++w) bm = fmaxf(bm, wmax[(it & 1) * N_CVT_WARPS + w]);
             // block scale from the largest |x| of the last `win` tiles (the cascade's memory): the chunk start states
             // of this tile are then bounded by the plan-time gain times that maximum, so they fit the fp16 operand of
             // the correction GEMM whatever the signal does
@@ -344,13 +348,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
             if (wm > 0.f && wm < 3.0e38f) (void)frexpf(wm, &ex);
             const int e = max(-100, min(100, a.xexp - ex));
             const float sx = ldexpf(1.0f, e);
-            if (ct == 0) tile_m[it % E_RING] = bm;
-#pragma unroll
+            if (ct == 0) {
+                tile_m[it % E_RING] = bm;
+                tile_e[it % E_RING] = e;
+            }
+            // pass 2 (rolled): fp32 -> fp16 hi + fp16 residual, into the swizzled operand regions of stage s
+            STC_WAIT(A_EMPTY(s), ((uint32_t)(it / NSTAGE) & 1u) ^ 1u, 0);
+            // chunk c = c_first + 4 i: its swizzle phase c & 7 alternates between two values
+            unsigned char *wbase = st + (2 * parity) * REGION + c_first * 128 + sub;
+            const uint32_t sw0 = (uint32_t)((colb ^ (c_first & 7)) << 4), sw1 = (uint32_t)((colb ^ ((c_first + 4) & 7)) << 4);
+#pragma unroll 2
             for (int i = 0; i < G_PER_THREAD; ++i) {
-                const int c = c_first + 4 * i;                                   // chunk = row of the operand region
-                const uint32_t off = (uint32_t)(c * 128 + ((colb ^ (c & 7)) << 4) + sub);
-                const float4 r = raw4[i];
-                const float v0 = r.x * sx, v1 = r.y * sx, v2 = r.z * sx, v3 = r.w * sx;
+                const float4 rv = reinterpret_cast<const float4 *>(raw)[ct + i * N_CVT];
+                const float v0 = rv.x * sx, v1 = rv.y * sx, v2 = rv.z * sx, v3 = rv.w * sx;
                 const __half2 h01 = __floats2half2_rn(v0, v1);
                 const __half2 h23 = __floats2half2_rn(v2, v3);
                 const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
@@ -361,13 +371,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
                 hv.y = *reinterpret_cast<const uint32_t *>(&h23);
                 lv.x = *reinterpret_cast<const uint32_t *>(&l01);
                 lv.y = *reinterpret_cast<const uint32_t *>(&l23);
-                *reinterpret_cast<uint2 *>(st + (2 * parity + 0) * REGION + off) = hv;
-                *reinterpret_cast<uint2 *>(st + (2 * parity + 1) * REGION + off) = lv;
+                unsigned char *w = wbase + i * 512 + ((i & 1) ? sw1 : sw0);
+                *reinterpret_cast<uint2 *>(w) = hv;
+                *reinterpret_cast<uint2 *>(w + REGION) = lv;
             }
-            if (ct == 0) tile_e[it % E_RING] = e;
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(A_FULL(s));
+            if (lane == 0) {
+                mbar_arrive(RAW_EMPTY(r));
+                mbar_arrive(A_FULL(s));
+            }
         }
     } else if (warp == MMA_WARP) {
         // =============================== bulk-TMA producer + MMA issuer ===============================
@@ -375,14 +388,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
         // tile's MMAs release, i.e. the wait for that stage ends exactly when the tensor pipe is ready for this
         // tile's MMAs (no separate producer warp: 16 warps keep 128 registers per thread).
         auto produce = [&](int64_t ptile, int pit) {
-            const int ps = pit % NSTAGE;
-            STC_WAIT(A_EMPTY(ps), ((uint32_t)(pit / NSTAGE) & 1u) ^ 1u, 0);
+            const int pr = pit % NRAW;
+            STC_WAIT(RAW_EMPTY(pr), ((uint32_t)(pit / NRAW) & 1u) ^ 1u, 0);
             if (elect_one()) {
                 if (tile_is_bulk(a, ptile)) {
-                    mbar_arrive_expect_tx(RAW_FULL(ps), STAGE_BYTES);
-                    bulk_g2s(base + ps * STAGE_BYTES, a.x + ptile * TILE, STAGE_BYTES, RAW_FULL(ps));
+                    mbar_arrive_expect_tx(RAW_FULL(pr), STAGE_BYTES);
+                    bulk_g2s(base + SM_RAW + pr * STAGE_BYTES, a.x + ptile * TILE, STAGE_BYTES, RAW_FULL(pr));
                 } else {
-                    mbar_arrive(RAW_FULL(ps));
+                    mbar_arrive(RAW_FULL(pr));
                 }
             }
             __syncwarp();
@@ -457,9 +470,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
         int next_prod = 0;
         auto top_up = [&](int need) {
             while (next_prod < n_it) {
-                const int ps = next_prod % NSTAGE;
-                const uint32_t par = ((uint32_t)(next_prod / NSTAGE) & 1u) ^ 1u;
-                if (next_prod > need && (next_prod >= need + NSTAGE || !mbar_test(A_EMPTY(ps), par))) break;
+                const int pr = next_prod % NRAW;
+                const uint32_t par = ((uint32_t)(next_prod / NRAW) & 1u) ^ 1u;
+                if (next_prod > need && !mbar_test(RAW_EMPTY(pr), par)) break;
                 produce(t_begin + next_prod, next_prod);
                 ++next_prod;
             }
@@ -483,7 +496,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
         int mstride;
         if constexpr (Z64) { MA128 = smat; MKS = smat + ND * ND; mstride = ND * ND; }
         else { MA128 = fold + 12 * FOLD_PITCH; MKS = fold + 13 * FOLD_PITCH; mstride = FOLD_PITCH; }
-        const float *es = esm + b * NCHUNK * EP;
+        float *es = esm + b * NCHUNK * EP;
         int it = b;
         for (int64_t tile = t_begin + b; tile < t_end; tile += 2, it += 2) {
             const uint32_t pb = (uint32_t)(it >> 1) & 1u;
@@ -515,8 +528,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
                     Mt = MKS + (st - 1) * mstride;
                     active = lane >= off;
                 } else {
-                    // the chain warp has consumed the previous aggregate / zero-state start states of this buffer
-                    STC_WAIT(Z_EMPTY(b), pb ^ 1u, 6);
 #pragma unroll
                     for (int k = 0; k < ND; ++k) {
                         o[k] = __shfl_up_sync(0xffffffffu, q[k], 1);
@@ -538,7 +549,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
 #pragma unroll
             for (int k = 0; k < ND; ++k) o[k] = zs[k];
             {
-                float *d0 = s0sm + (b * NCHUNK + 2 * lane) * EP, *d1 = d0 + EP;
+                // the zero-state start states replace this lane's two carry rows (same rows, same lane: in place)
+                float *d0 = es + (2 * lane) * EP, *d1 = d0 + EP;
 #pragma unroll
                 for (int k = 0; k < ND; k += 4) {
                     *reinterpret_cast<float4 *>(d0 + k) = make_float4((float)o[k], (float)o[k + 1], (float)o[k + 2], (float)o[k + 3]);
@@ -546,10 +558,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
                 }
             }
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(Z_READY(b));
-                mbar_arrive(ESM_EMPTY(b));
-            }
+            if (lane == 0) mbar_arrive(Z_READY(b));
         }
     } else if (warp == CHAIN_WARP) {
         // =============================== serial chain between tiles ===============================
@@ -585,7 +594,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
 #pragma unroll
             for (int k = 0; k < ND; ++k) nxt[k] = aggsm[b * 16 + k];
             if (!a.at_zero) mv_acc<ND>(nxt, MAT, s_in);
-            const float *d0 = s0sm + (b * NCHUNK + 2 * lane) * EP, *d1 = d0 + EP;
+            const float *d0 = esm + (b * NCHUNK + 2 * lane) * EP, *d1 = d0 + EP;
 #pragma unroll
             for (int k = 0; k < ND; k += 4) {
                 const float4 z0 = *reinterpret_cast<const float4 *>(d0 + k), z1 = *reinterpret_cast<const float4 *>(d1 + k);
@@ -593,7 +602,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
                 h1[k] += z1.x; h1[k + 1] += z1.y; h1[k + 2] += z1.z; h1[k + 3] += z1.w;     //                     chunk 2l+1
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(Z_EMPTY(b));
+            if (lane == 0) mbar_arrive(ESM_EMPTY(b));            // carries / start states / aggregate of this buffer consumed
             // the two chunk rows of the correction operand: fp16 hi (k 0..15) and residual (k 16..31) of s_d * sfac[d] * 2^e_x
             STC_WAIT(SOP_EMPTY(b), pb ^ 1u, 7);
             {
