@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
                 tile_e[it % E_RING] = e;
             }
             // pass 2 (rolled): fp32 -> fp16 hi + fp16 residual, into the swizzled operand regions of stage s
-            STC_WAIT(A_EMPTY(s), ((uint32_t)(it / NSTAGE) & 1u) ^ 1u, 0);
+            STC_WAIT(A_EMPTY(s), ((uint32_t)(it / NSTAGE) & 1u) ^ 1u, 10);
             // chunk c = c_first + 4 i: its swizzle phase c & 7 alternates between two values
             unsigned char *wbase = st + (2 * parity) * REGION + c_first * 128 + sub;
             const uint32_t sw0 = (uint32_t)((colb ^ (c_first & 7)) << 4), sw1 = (uint32_t)((colb ^ ((c_first + 4) & 7)) << 4);
@@ -408,8 +408,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
         auto eread = [&](int eit) {
             const int eb = eit & 1;
             const uint32_t epb = (uint32_t)(eit >> 1) & 1u;
-            STC_WAIT(ESM_EMPTY(eb), epb ^ 1u, 3);
-            STC_WAIT(E_FULL(eb), epb, 4);
+            STC_WAIT(ESM_EMPTY(eb), epb ^ 1u, 13);
+            STC_WAIT(E_FULL(eb), epb, 14);
             tc_fence_after();
             float *es = esm + eb * NCHUNK * EP;
             const float sc = ldexpf(rowinv, -tile_e[eit % E_RING]);
@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
             __syncwarp();
             if (lane == 0) mbar_arrive(ESM_EMPTY(b));            // carries / start states / aggregate of this buffer consumed
             // the two chunk rows of the correction operand: fp16 hi (k 0..15) and residual (k 16..31) of s_d * sfac[d] * 2^e_x
-            STC_WAIT(SOP_EMPTY(b), pb ^ 1u, 7);
+            STC_WAIT(SOP_EMPTY(b), pb ^ 1u, 17);
             {
                 const float px = ldexpf(1.0f, tile_e[it % E_RING]);
                 unsigned char *sop = sm + SM_SOP + b * SOP_BYTES;
@@ -696,7 +696,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
             const uint64_t xe_hi = make_desc_sw128(st + 0 * REGION), xe_lo = make_desc_sw128(st + 1 * REGION);
             const uint64_t xo_hi = make_desc_sw128(st + 2 * REGION), xo_lo = make_desc_sw128(st + 3 * REGION);
             STC_WAIT(D_EMPTY(yb), ((uint32_t)(yit >> 1) & 1u) ^ 1u, 4);
-            STC_WAIT(A_FULL(s), (uint32_t)(yit / NSTAGE) & 1u, 2);
+            STC_WAIT(A_FULL(s), (uint32_t)(yit / NSTAGE) & 1u, 12);
             tc_fence_after();
             if (elect_one()) {
                 if (!(DBG && (a.dbg & 1))) {

@@ -19,13 +19,15 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 // Bounded wait: a protocol bug must end in a trap, never in a hung GPU.  The bound is WALL-CLOCK time
-// (%globaltimer, 20 s), not a poll count, so profiler replay, preemption or MPS time-slicing cannot
+// (%globaltimer, 10 s), not a poll count, so profiler replay, preemption or MPS time-slicing cannot
 // false-trap a healthy kernel.
 __device__ __forceinline__ uint64_t global_ns() {
     uint64_t t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+// plain try_wait: a suspend-time hint (tried: 8 us) makes waiting warps cheaper for their scheduler but wakes
+// them later -- measured slower on both the FIR (1.08 -> 1.09 ms) and the SOS kernel (0.55 -> 0.58 ms)
 __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
     uint32_t done;
     asm volatile(
@@ -47,10 +49,19 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
 }
 // the failure path lives out of line: ~25 wait sites per kernel would otherwise each carry a printf call sequence
 // (instruction-cache footprint of the warp-specialised kernels)
-static __device__ __noinline__ void mbar_timeout(int who) {
-    printf("b200dsp tensor-core kernel: mbarrier timeout (role %d, block %d)\n", who, (int)blockIdx.x);
+static __device__ __noinline__ void mbar_timeout(int who, uint32_t bar, uint32_t parity) {
+    if ((threadIdx.x & 31) == 0)
+        printf("b200dsp tensor-core kernel: mbarrier timeout (role %d, block %d, warp %d, barrier 0x%x parity %u)\n", who,
+               (int)blockIdx.x, (int)(threadIdx.x >> 5), bar, parity);
+    // give the other stuck roles a moment to report before the trap takes the kernel down
+    const uint64_t t0 = global_ns();
+    while (global_ns() - t0 < 200000000ull) {}
     __trap();
 }
+// (keep this loop minimal: waiting warps share their scheduler and the instruction cache with working warps --
+// a two-stage report inside the loop cost the SOS kernel 15 %)
+// Measured on one box, FIR headline / SOS cfg4: count-bounded poll 1.109 / 0.685 ms, this loop 1.098 / 0.567 ms,
+// this loop + nanosleep(32 | 128) 1.101 / 0.566 ms.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int who) {
     uint64_t t0 = 0;
     for (uint32_t spin = 1;; ++spin) {
@@ -58,10 +69,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int who
         if ((spin & 0xFFFFu) == 0) {
             const uint64_t t = global_ns();
             if (t0 == 0) t0 = t;
-            else if (t - t0 > 20000000000ull) break;
+            else if (t - t0 > 10000000000ull) break;
         }
     }
-    mbar_timeout(who);
+    mbar_timeout(who, bar, parity);
 }
 // one elected lane of a converged warp (lets ptxas emit UTCHMMA / UBLKCP without a lane loop)
 __device__ __forceinline__ bool elect_one() {
