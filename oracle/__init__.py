@@ -298,7 +298,8 @@ def _baseline_chunk(task):
     """Worker: one halo-chunk of the reference FIR call on its own seeded complex64 data.
     The input is generated once per worker and cached so that timed passes measure
     ``np.convolve`` (what lfilter's FIR branch executes, in complex128) and nothing else."""
-    seed, n, b_bytes = task
+    seed, n, b_bytes = task[:3]
+    kind = task[3] if len(task) > 3 else "port"
     b = np.frombuffer(b_bytes, dtype=np.float64)
     key = (seed, n)
     x = _BASE_CACHE.get(key)
@@ -309,7 +310,12 @@ def _baseline_chunk(task):
         _BASE_CACHE.clear()
         _BASE_CACHE[key] = x
     K = len(b)
-    y = fir_filter(b, x[K - 1:], hist=x[:K - 1])         # np.convolve in complex128
+    if kind == "scipy":
+        # the reference's literal call (multirate_helper.py:108) on the chunk with its halo in front
+        from scipy import signal
+        y = signal.lfilter(b, [1], x)[K - 1:]
+    else:
+        y = fir_filter(b, x[K - 1:], hist=x[:K - 1])     # np.convolve in complex128
     return float(np.abs(y[:16]).sum())
 
 
@@ -317,14 +323,21 @@ class FirCpuBaseline:
     """All-cores run of the reference's FIR arithmetic on halo-chunks:
     ``cores`` worker processes, each filtering ``chunk`` complex64 samples per pass."""
 
-    def __init__(self, b, cores=None, chunk=1 << 21):
+    def __init__(self, b, cores=None, chunk=1 << 21, kind="auto"):
         import multiprocessing as mp
         import os
+        if kind == "auto":
+            try:
+                from scipy import signal  # noqa: F401
+                kind = "scipy"
+            except Exception:
+                kind = "port"
+        self.kind = kind              # "scipy": scipy.signal.lfilter(b,[1],x) itself; "port": the np.convolve restatement
         self.cores = cores or len(os.sched_getaffinity(0))
         self.chunk = chunk
         self.b_bytes = np.asarray(b, dtype=np.float64).tobytes()
         self.pool = mp.get_context("fork").Pool(self.cores)      # created before any CUDA init
-        self.tasks = [(1000 + i, chunk, self.b_bytes) for i in range(self.cores)]
+        self.tasks = [(1000 + i, chunk, self.b_bytes, kind) for i in range(self.cores)]
         self.samples_per_pass = self.cores * chunk
         self.run_pass()                                    # generate inputs, warm numpy
 

@@ -578,6 +578,7 @@ static size_t sos_scan_area_bytes(int dtype, int64_t n_rate)
     return 2 * a + (size_t)n_tiles * per_tile * SOS_NT + 256;
 }
 
+
 // resample.cu
 int resample_up_scaled(int dtype, const void *x, void *y, int64_t n, int32_t L, double gain, cudaStream_t st);
 int resample_dn(int dtype, const void *x, void *y, int64_t n_out, int32_t M, cudaStream_t st);
@@ -596,8 +597,14 @@ static bool sos_tc_path(const b200dsp_sos_plan_impl *p, int dtype, int64_t n_rat
 {
     if (dtype != B200DSP_F32 || g_sos_variant == 1) return false;
     if (M > 1 && p->groups.size() > 2) return false;      // full-rate intermediates would need two scratch streams
+    // Cascades with poles very close to the unit circle (more than one warm-up tile) always take the tensor-core
+    // kernel when they can: its in-tile scan runs in float64 and the zero-state part is a direct sum, whereas the
+    // float32 recurrence of the scan kernels loses the 1e-4 bar there (ten-band equaliser: 1.1e-4 vs 4e-6).
+    bool force = g_sos_variant == 2;
     for (const SosGroup &g : p->groups)
-        if (!stc_usable(g.tc, n_rate, p->sm_count, g_sos_variant == 2)) return false;
+        if (g.tc.ok && g.tc.warm_tiles > 1) force = true;
+    for (const SosGroup &g : p->groups)
+        if (!stc_usable(g.tc, n_rate, p->sm_count, force)) return false;
     return true;
 }
 
@@ -609,6 +616,19 @@ static int sos_run_tc(const b200dsp_sos_plan_impl *p, const float *x, float *y, 
     const int64_t n_rate = n * L, n_out = n_rate / M;
     const size_t ng = p->groups.size();
     float *tmp = reinterpret_cast<float *>(ws);
+    // A long interpolating call with a single group stages the (x L) zero-stuffed stream once in the workspace with
+    // the streaming index-map kernel and runs the cascade on bulk-TMA tiles (the fused zero stuffing has the
+    // converter warps fetch every tile themselves: fine for short calls, 3x slower on long ones).
+    const float *src0 = x;
+    int64_t n_in0 = n;
+    int32_t L0 = L;
+    if (L > 1 && ng == 1 && n_rate >= SOS_STAGE_MIN) {
+        int rc = resample_up_scaled(B200DSP_F32, x, tmp, n, L, (double)L, st);
+        if (rc != B200DSP_OK) return rc;
+        src0 = tmp;
+        n_in0 = n_rate;
+        L0 = 1;
+    }
     size_t sec0 = 0;
     for (size_t gi = 0; gi < ng; ++gi) {
         const SosGroup &g = p->groups[gi];
@@ -616,11 +636,11 @@ static int sos_run_tc(const b200dsp_sos_plan_impl *p, const float *x, float *y, 
         // ping-pong between y and the workspace so that the last group lands in y (never in place: a block's
         // warm-up tiles are read from its neighbour's range)
         auto out_of = [&](size_t k) -> float * { return ((ng - 1 - k) % 2 == 0 && (M == 1 || k + 1 == ng)) ? y : tmp; };
-        const float *src = first ? x : out_of(gi - 1);
+        const float *src = first ? src0 : out_of(gi - 1);
         float *dst = out_of(gi);
         const float *zig = zi ? static_cast<const float *>(zi) + sec0 * 2 : nullptr;
         float *zfg = zf ? static_cast<float *>(zf) + sec0 * 2 : nullptr;
-        int rc = launch_sos_tc(g.tc, src, dst, first ? n : n_rate, n_rate, last ? n_out : n_rate, first ? L : 1,
+        int rc = launch_sos_tc(g.tc, src, dst, first ? n_in0 : n_rate, n_rate, last ? n_out : n_rate, first ? L0 : 1,
                                last ? M : 1, zig, zfg, p->sm_count, st);
         if (rc != B200DSP_OK) return rc;
         sec0 += g.nsec_real;

@@ -18,6 +18,38 @@ DEFAULT_CHUNK = 1 << 24      # samples per chunk (128 MiB of complex64)
 NBUF = 3
 
 
+def bind_to_gpu_numa(device_index: int):
+    """Pin the calling process to the CPU cores of the NUMA node its GPU hangs off (PCI topology in sysfs), so that
+    pinned staging buffers are first-touched in that node's memory and the copy threads run next to the GPU.
+    One process per GPU (torchrun): without this every rank allocates on node 0 and the host<->device copies of
+    several ranks share one memory controller / one PCIe root.  Returns a dict describing what was done."""
+    import os
+    info = {"node": None, "cpus": None}
+    try:
+        prop = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return info
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info = {"node": node, "cpus": len(allowed)}
+    except Exception:           # noqa: BLE001 -- topology files missing (containers): leave the affinity alone
+        pass
+    return info
+
+
 class _Pipe:
     """Device staging buffers + streams, cached per (device, dtype, chunk, ntaps)."""
 
