@@ -14,7 +14,11 @@
  *     CUDA device; `*_host` pointers are host pointers read synchronously during the call.
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All work
  *     is enqueued asynchronously on it; nothing is allocated or synchronised inside the
- *     filter calls (plans own their small coefficient buffers, created once).
+ *     filter calls: plans own their coefficient buffers and every kernel table (tensor-core tap
+ *     matrices, scan matrices), all built in the *_plan_create call, and are read-only afterwards
+ *     -- one plan may be used from several threads and inside CUDA-graph capture.  (The only host
+ *     state a filter call may add is a mutex-guarded cache of scan-matrix powers the first time an
+ *     SOS plan sees a new call length on the float64 / complex path; no device allocation.)
  *   - return value: 0 = OK, negative = error (B200DSP_E_*); b200dsp_last_error() gives the
  *     thread-local message.  No exception ever crosses this boundary.
  *   - sample counts are int64_t (a 2^31-sample stream does not fit int32).
@@ -30,7 +34,7 @@
 extern "C" {
 #endif
 
-#define B200DSP_VERSION 100 /* 0.1.0 */
+#define B200DSP_VERSION 200 /* 0.2.0 */
 
 /* sample dtypes (complex = interleaved re,im; filter coefficients are always real) */
 enum {
@@ -71,6 +75,13 @@ int32_t b200dsp_fir_plan_ntaps(const b200dsp_fir_plan *plan);
  * through FFT frames. */
 int b200dsp_fir_filter(const b200dsp_fir_plan *plan, int dtype, const void *x, const void *hist,
                        void *y, int64_t n, void *stream);
+
+/* The same for `rows` independent streams of n samples each (row r at x + r*x_row_stride samples, output at
+ * y + r*y_row_stride), zero initial state per row: scipy.signal.lfilter filters the LAST axis of an N-D array,
+ * which is what multirate_FIR.filter hands it (multirate_helper.py:108).  One C call; the rows are queued back to
+ * back on `stream`. */
+int b200dsp_fir_filter_batch(const b200dsp_fir_plan *plan, int dtype, const void *x, void *y, int64_t rows,
+                             int64_t n, int64_t x_row_stride, int64_t y_row_stride, void *stream);
 
 /* y[L*m+r] = L * sum_q b[L*q+r] * xe[m-q], m in [0,n): n*L outputs.
  * Replaces multirate_FIR.up -> lfilter(b,[1], L*upsample(x,L))  (multirate_helper.py:112-118)
@@ -116,6 +127,11 @@ int b200dsp_sos_filter(const b200dsp_sos_plan *plan, int dtype, const void *x, v
                        int32_t L, int32_t M, const void *zi, void *zf, void *ws, size_t ws_bytes,
                        void *stream);
 
+/* `rows` independent streams (last axis of an N-D array, as sosfilt filters it), L = M = 1, zero initial state per
+ * row; ws as for a single n-sample call (the rows share it). */
+int b200dsp_sos_filter_batch(const b200dsp_sos_plan *plan, int dtype, const void *x, void *y, int64_t rows, int64_t n,
+                             int64_t x_row_stride, int64_t y_row_stride, void *ws, size_t ws_bytes, void *stream);
+
 /* ------------------------------------------------------------------ rate change --------
  * y[i*L] = x[i], zeros elsewhere; n*L outputs.  Replaces sigsys.upsample (sigsys.py:3031-3053).
  * Pure index map: bit exact.  (The reference widens to >= float64; that dtype policy lives
@@ -126,6 +142,12 @@ int b200dsp_upsample(int dtype, const void *x, void *y, int64_t n, int32_t L, vo
  * Pure index map: bit exact. */
 int b200dsp_downsample(int dtype, const void *x, void *y, int64_t n, int32_t M, int32_t p,
                        void *stream);
+
+/* y = a + j*b, n samples.  dtype_in = dtype of a and b: real (F32/F64: y is the complex stream (a, b)) or complex
+ * (C64/C128: y = (a.re - b.im, a.im + b.re)).  Second half of a complex-tap FIR: scipy.signal.lfilter accepts complex
+ * b (multirate_helper.py:108 passes self.b through); by linearity lfilter(br + j*bi, 1, x) = lfilter(br,1,x) +
+ * j*lfilter(bi,1,x), i.e. two real-tap plans and this combination. */
+int b200dsp_combine_complex(int dtype_in, const void *a, const void *b, void *y, int64_t n, void *stream);
 
 /* ------------------------------------------------------------------ diagnostics --------
  * Number of kernel launches issued through this library by the calling thread since the

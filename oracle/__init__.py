@@ -107,11 +107,15 @@ def fir_filter(b, x, hist=None, backend="numpy"):
     overlap-save halo used by the sharded path; ``None`` = zeros, which is
     the reference's stateless behaviour.
     """
-    b = np.asarray(b, dtype=np.float64)
+    b = np.asarray(b)
+    # complex taps (lfilter accepts them): numpy path only, the result is complex128
+    b = b.astype(np.complex128) if np.iscomplexobj(b) else b.astype(np.float64)
     x = np.asarray(x)
     if x.ndim != 1:
         return np.apply_along_axis(lambda v: fir_filter(b, v, None, backend), -1, x)
     dt = result_dtype(b, x)
+    if np.iscomplexobj(b):
+        backend = "numpy"
     n, K = x.shape[0], b.shape[0]
     if backend == "c" and have_c():
         xs, xv, nch = _as_real_view(x, dt)
@@ -153,7 +157,10 @@ def downsample(x, M, p=0):
 
 def fir_up(b, x, L, backend="numpy"):
     """``multirate_FIR.up`` (multirate_helper.py:112-118)."""
-    b = np.asarray(b, dtype=np.float64)
+    b = np.asarray(b)
+    if np.iscomplexobj(b):
+        return fir_filter(b, L * upsample(x, L))
+    b = b.astype(np.float64)
     x = np.asarray(x)
     if backend == "c" and have_c():
         dt = result_dtype(b, x)
@@ -166,7 +173,10 @@ def fir_up(b, x, L, backend="numpy"):
 
 def fir_dn(b, x, M, backend="numpy"):
     """``multirate_FIR.dn`` (multirate_helper.py:121-127)."""
-    b = np.asarray(b, dtype=np.float64)
+    b = np.asarray(b)
+    if np.iscomplexobj(b):
+        return downsample(fir_filter(b, x), M)
+    b = b.astype(np.float64)
     x = np.asarray(x)
     if backend == "c" and have_c():
         dt = result_dtype(b, x)

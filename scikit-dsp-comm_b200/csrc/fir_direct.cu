@@ -17,6 +17,7 @@
 // per-lane window accesses are bank-conflict free.  Results leave through a shared-memory
 // transpose so global stores are fully coalesced.
 #include "common.cuh"
+#include <vector>
 
 namespace b200dsp {
 
@@ -256,13 +257,14 @@ struct b200dsp_fir_plan_impl {
     int32_t ntaps;
     float *taps_f32;
     double *taps_f64;
-    double *taps_host;   // host copy (lazy construction of tensor-core tap matrices)
+    double *taps_host;   // host copy
     void *tc2_amat;      // taps-stationary tensor-core path: 128 x 320 fp16 matrix for TMEM (or NULL)
     int32_t tc2_sb_exp;
     // float32 tensor-core paths (fir_tc_real.cu): tap matrices per (mode, factor), built on first use
-    void *tcr_mat[4][5];
+    void *tcr_mat[4][5];      // pointers into tcr_pool
     int32_t tcr_sb[4][5];
-    int8_t tcr_state[4][5];   // 0 not built yet, 1 ready, -1 unsupported for this filter
+    int8_t tcr_state[4][5];   // 1 ready, otherwise this (mode, factor) does not fit the tensor-core kernel
+    void *tcr_pool;           // one allocation for all of them (plan_create)
     int32_t sm_count;
 };
 
@@ -336,6 +338,68 @@ static int launch_fir(const b200dsp_fir_plan_impl *p, const void *x, const void 
     return B200DSP_OK;
 }
 
+// ---- last resort: no staging limits ---------------------------------------------------------------------
+// One thread per output, taps and samples straight from global memory (L1 / L2 keep them).  Serves the shapes
+// whose staging does not fit fir_poly_kernel's shared-memory tile: decimation by more than ~50 (the reference
+// accepts any M, multirate_helper.py:121-127) or filters of many thousand taps.  Same accumulation order as the
+// oracle's direct sum (k ascending), float64 accumulators for the float64 dtypes, float32 otherwise.
+template <typename S, typename C>
+__global__ void __launch_bounds__(256) fir_generic_kernel(const FirArgs<S, C> a, int64_t n_out)
+{
+    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n_out) return;
+    // output o: up -> (m, r) = (o / L, o % L), taps r, r+L, ... against x[m], x[m-1], ...; filter / dn: all taps
+    // against x[M o - k]
+    const int64_t m = (a.L > 1) ? o / a.L : o;
+    const int r = (a.L > 1) ? (int)(o - m * a.L) : 0;
+    const int64_t pos0 = (a.L > 1) ? m : o * (int64_t)a.M;
+    const C gain = (a.L > 1) ? (C)a.L : (C)1;
+    S acc = zero_of(S());
+    for (int t = r, q = 0; t < a.ntaps; t += a.L, ++q) {
+        const int64_t pos = pos0 - q;
+        S v;
+        if (pos >= 0) {
+            if (pos >= a.n_in) continue;
+            v = a.x[pos];
+        } else {
+            const int64_t h = (int64_t)a.hist_len + pos;
+            if (a.hist == nullptr || h < 0) break;              // zero initial state from here on
+            v = a.hist[h];
+        }
+        tap_fma(acc, a.taps[t] * gain, v);
+    }
+    a.y[o] = acc;
+}
+
+template <typename S>
+static int launch_fir_generic(const b200dsp_fir_plan_impl *p, const void *x, const void *hist, void *y,
+                              int64_t n, int64_t n_m, int32_t L, int32_t M, int32_t hist_len, cudaStream_t stream)
+{
+    using C = typename Sample<S>::C;
+    FirArgs<S, C> a;
+    a.x = static_cast<const S *>(x);
+    a.hist = static_cast<const S *>(hist);
+    a.y = static_cast<S *>(y);
+    a.taps = sizeof(C) == 4 ? reinterpret_cast<const C *>(p->taps_f32) : reinterpret_cast<const C *>(p->taps_f64);
+    a.n_in = n;
+    a.n_m = n_m;
+    a.ntaps = p->ntaps;
+    a.kq = 0;
+    a.hist_len = hist_len;
+    a.L = L;
+    a.M = M;
+    a.lg = 1;
+    const int64_t n_out = n_m * L;
+    const int64_t blocks = (n_out + 255) / 256;
+    if (blocks > 2147483647LL) {
+        set_error("fir: too many blocks (%lld)", (long long)blocks);
+        return B200DSP_E_UNSUPPORTED;
+    }
+    fir_generic_kernel<S, C><<<(unsigned)blocks, 256, 0, stream>>>(a, n_out);
+    B200_CHECK_LAUNCH("fir_generic_kernel");
+    return B200DSP_OK;
+}
+
 // Try progressively smaller tiles until the staging fits in shared memory.
 template <typename S, int R, bool PK = false>
 static int launch_fir_fit(const b200dsp_fir_plan_impl *p, const void *x, const void *hist, void *y,
@@ -354,8 +418,8 @@ static int launch_fir_fit(const b200dsp_fir_plan_impl *p, const void *x, const v
     rc = launch_fir<S, R, 64, PK>(p, x, hist, y, n, n_m, L, M, hist_len, stream);
     if (rc != B200DSP_E_UNSUPPORTED) return rc;
     rc = launch_fir<S, R, 32, PK>(p, x, hist, y, n, n_m, L, M, hist_len, stream);
-    if (rc == B200DSP_E_UNSUPPORTED)
-        set_error("fir: filter (%d taps, L=%d, M=%d) too long for on-chip staging", p->ntaps, L, M);
+    if (rc == B200DSP_E_UNSUPPORTED)      // staging does not fit even the smallest tile: unstaged kernel
+        rc = launch_fir_generic<S>(p, x, hist, y, n, n_m, L, M, hist_len, stream);
     return rc;
 }
 
@@ -398,32 +462,10 @@ static int launch_fir_up_short(const b200dsp_fir_plan_impl *p, const void *x, co
     return B200DSP_OK;
 }
 
-// Lazily build (and cache in the plan) the TMEM tap matrices of one float32 tensor-core mode.
-static bool tcr_ready(b200dsp_fir_plan_impl *p, int mode, int P)
-{
-    if (p->tcr_state[mode][P] == 0) {
-        p->tcr_state[mode][P] = -1;
-        const int nb = tcr_matrix_bytes(mode, P);
-        unsigned char *hb = new unsigned char[nb];
-        int sb = 0;
-        if (tcr_build(p->taps_host, p->ntaps, mode, P, hb, &sb) == 0) {
-            void *d = nullptr;
-            // cudaMemcpy from pageable memory may return before the DMA has landed; the consumers run on
-            // non-blocking streams, so wait for the NULL stream explicitly
-            if (cudaMalloc(&d, nb) == cudaSuccess &&
-                cudaMemcpy(d, hb, nb, cudaMemcpyHostToDevice) == cudaSuccess &&
-                cudaStreamSynchronize(0) == cudaSuccess) {
-                p->tcr_mat[mode][P] = d;
-                p->tcr_sb[mode][P] = sb;
-                p->tcr_state[mode][P] = 1;
-            } else if (d) {
-                cudaFree(d);
-            }
-        }
-        delete[] hb;
-    }
-    return p->tcr_state[mode][P] == 1;
-}
+// The TMEM tap matrices of the float32 tensor-core modes (filter; up / dn by 2..4) are all built in
+// b200dsp_fir_plan_create into one device allocation: filter calls allocate nothing, synchronise nothing and
+// never write to the plan (include/b200dsp.h contract; plans can be shared between threads and captured in graphs).
+static bool tcr_ready(const b200dsp_fir_plan_impl *p, int mode, int P) { return p->tcr_state[mode][P] == 1; }
 
 static int fir_dispatch(const b200dsp_fir_plan_impl *p, int dtype, const void *x, const void *hist,
                         void *y, int64_t n, int64_t n_m, int32_t L, int32_t M, int32_t hist_len,
@@ -438,7 +480,7 @@ static int fir_dispatch(const b200dsp_fir_plan_impl *p, int dtype, const void *x
         const int mode = (L > 1) ? 2 : (M > 1 ? 3 : 1);
         const int P = (L > 1) ? L : (M > 1 ? M : 1);
         if (v == 0 && aligned && P <= 4 && n_m >= 16384 &&
-            tcr_ready(const_cast<b200dsp_fir_plan_impl *>(p), mode, P))
+            tcr_ready(p, mode, P))
             return launch_fir_tc_real(mode, P, x, hist, y, n, hist_len, p->tcr_mat[mode][P],
                                       p->tcr_sb[mode][P], p->ntaps, p->sm_count, s);
         }
@@ -537,6 +579,35 @@ int b200dsp_fir_plan_create(const double *taps_host, int32_t ntaps, b200dsp_fir_
         }
         delete[] h2;
     }
+    // float32 tensor-core tap matrices: mode 1 filter, 2 up(P), 3 dn(P), P = 2..4 -- every one that fits the filter
+    p->tcr_pool = nullptr;
+    if (e == cudaSuccess) {
+        std::vector<unsigned char> pool;
+        struct Slot { int mode, P; size_t off; };
+        std::vector<Slot> slots;
+        for (int mode = 1; mode <= 3; ++mode)
+            for (int P = (mode == 1 ? 1 : 2); P <= (mode == 1 ? 1 : 4); ++P) {
+                const int nb = tcr_matrix_bytes(mode, P);
+                const size_t off = (pool.size() + 255) & ~(size_t)255;
+                pool.resize(off + nb);
+                int sb = 0;
+                if (tcr_build(taps_host, ntaps, mode, P, pool.data() + off, &sb) == 0) {
+                    slots.push_back({mode, P, off});
+                    p->tcr_sb[mode][P] = sb;
+                } else {
+                    pool.resize(off);
+                }
+            }
+        if (!slots.empty()) {
+            e = cudaMalloc(&p->tcr_pool, pool.size());
+            if (e == cudaSuccess) e = cudaMemcpy(p->tcr_pool, pool.data(), pool.size(), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess)
+                for (const Slot &sl : slots) {
+                    p->tcr_mat[sl.mode][sl.P] = static_cast<unsigned char *>(p->tcr_pool) + sl.off;
+                    p->tcr_state[sl.mode][sl.P] = 1;
+                }
+        }
+    }
     // cudaMemcpy from pageable host memory may return before the DMA to the device has completed; kernels
     // are launched on arbitrary (non-blocking) streams, so make the uploads visible to all of them now
     if (e == cudaSuccess) e = cudaStreamSynchronize(0);
@@ -545,6 +616,7 @@ int b200dsp_fir_plan_create(const double *taps_host, int32_t ntaps, b200dsp_fir_
         cudaFree(p->taps_f32);
         cudaFree(p->taps_f64);
         cudaFree(p->tc2_amat);
+        cudaFree(p->tcr_pool);
         delete[] p->taps_host;
         delete p;
         return B200DSP_E_CUDA;
@@ -559,8 +631,7 @@ void b200dsp_fir_plan_destroy(b200dsp_fir_plan *plan)
     cudaFree(plan->taps_f32);
     cudaFree(plan->taps_f64);
     cudaFree(plan->tc2_amat);
-    for (int m = 0; m < 4; ++m)
-        for (int q = 0; q < 5; ++q) cudaFree(plan->tcr_mat[m][q]);
+    cudaFree(plan->tcr_pool);
     delete[] plan->taps_host;
     delete plan;
 }
@@ -606,6 +677,30 @@ int b200dsp_fir_dn(const b200dsp_fir_plan *plan, int dtype, const void *x, const
     int64_t n_m = n / M;
     if (n_m == 0) return B200DSP_OK;
     return fir_dispatch(plan, dtype, x, hist, y, n, n_m, 1, M, plan->ntaps - 1, (cudaStream_t)stream);
+}
+
+int b200dsp_fir_filter_batch(const b200dsp_fir_plan *plan, int dtype, const void *x, void *y, int64_t rows,
+                             int64_t n, int64_t x_row_stride, int64_t y_row_stride, void *stream)
+{
+    if (!plan || rows < 0 || n < 0 || x_row_stride < n || y_row_stride < n || (rows > 0 && n > 0 && (!x || !y))) {
+        set_error("fir_filter_batch: bad argument");
+        return B200DSP_E_BADARG;
+    }
+    size_t es = 0;
+    switch (dtype) {
+    case B200DSP_F32: es = 4; break;
+    case B200DSP_F64: es = 8; break;
+    case B200DSP_C64: es = 8; break;
+    case B200DSP_C128: es = 16; break;
+    default: set_error("fir_filter_batch: bad dtype code %d", dtype); return B200DSP_E_DTYPE;
+    }
+    for (int64_t r = 0; r < rows && n > 0; ++r) {
+        const int rc = fir_dispatch(plan, dtype, static_cast<const char *>(x) + (size_t)r * x_row_stride * es, nullptr,
+                                    static_cast<char *>(y) + (size_t)r * y_row_stride * es, n, n, 1, 1,
+                                    plan->ntaps - 1, (cudaStream_t)stream);
+        if (rc != B200DSP_OK) return rc;
+    }
+    return B200DSP_OK;
 }
 
 void b200dsp_set_fir_variant(int variant) { g_fir_variant = variant; }

@@ -147,7 +147,52 @@ int resample_dn(int dtype, const void *x, void *y, int64_t n_out, int32_t M, cud
 
 using namespace b200dsp;
 
+// y = a + j b : the two real-tap passes of a complex-tap FIR (lfilter accepts complex b; by linearity
+// lfilter(br + j bi, 1, x) = lfilter(br, 1, x) + j lfilter(bi, 1, x)).  CIN: a, b complex (complex stream) or real.
+template <typename R, typename C2, bool CIN>
+__global__ void __launch_bounds__(256) combine_complex_kernel(const void *a, const void *b, C2 *__restrict__ y, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    C2 o;
+    if (CIN) {
+        const C2 u = static_cast<const C2 *>(a)[i], v = static_cast<const C2 *>(b)[i];
+        o.x = u.x - v.y;
+        o.y = u.y + v.x;
+    } else {
+        o.x = static_cast<const R *>(a)[i];
+        o.y = static_cast<const R *>(b)[i];
+    }
+    y[i] = o;
+}
+
 extern "C" {
+
+int b200dsp_combine_complex(int dtype_in, const void *a, const void *b, void *y, int64_t n, void *stream)
+{
+    if (n < 0 || (n > 0 && (!a || !b || !y))) {
+        set_error("combine_complex: bad argument");
+        return B200DSP_E_BADARG;
+    }
+    if (n == 0) return B200DSP_OK;
+    const int64_t blocks = (n + 255) / 256;
+    if (blocks > 2147483647LL) {
+        set_error("combine_complex: too many blocks");
+        return B200DSP_E_UNSUPPORTED;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype_in) {
+    case B200DSP_F32: combine_complex_kernel<float, float2, false><<<(unsigned)blocks, 256, 0, st>>>(a, b, (float2 *)y, n); break;
+    case B200DSP_F64: combine_complex_kernel<double, double2, false><<<(unsigned)blocks, 256, 0, st>>>(a, b, (double2 *)y, n); break;
+    case B200DSP_C64: combine_complex_kernel<float, float2, true><<<(unsigned)blocks, 256, 0, st>>>(a, b, (float2 *)y, n); break;
+    case B200DSP_C128: combine_complex_kernel<double, double2, true><<<(unsigned)blocks, 256, 0, st>>>(a, b, (double2 *)y, n); break;
+    default:
+        set_error("combine_complex: bad dtype code %d", dtype_in);
+        return B200DSP_E_DTYPE;
+    }
+    B200_CHECK_LAUNCH("combine_complex_kernel");
+    return B200DSP_OK;
+}
 
 int b200dsp_upsample(int dtype, const void *x, void *y, int64_t n, int32_t L, void *stream)
 {

@@ -22,6 +22,8 @@
 // write (element-wise path), so multirate_IIR.up/.dn never materialise the full-rate stream.
 #include "common.cuh"
 #include "sos_tc.cuh"
+#include <map>
+#include <mutex>
 #include <type_traits>
 #include <vector>
 
@@ -436,12 +438,16 @@ struct SosGroup {
     float *mats_f32;                   // device [SOS_LEVELS][D*D]: A^(SOS_LC * 2^j)
     double *mats_f64;
     StcTables tc;                      // tensor-core single-pass kernel tables (float32 streams, sos_tc.cu)
+    // tile-level scan matrices (A^T)^(run 2^j) per distinct `run` (= tiles per thread of the tile-scan block, a
+    // function of the call length): computed once, then read-only.  shared_ptr-free: the map lives as long as the plan.
+    mutable std::map<int64_t, std::vector<double>> k2_cache;
 };
 
 struct b200dsp_sos_plan_impl {
     int nsec;
     int sm_count;
     std::vector<SosGroup> groups;
+    mutable std::mutex k2_mutex;       // guards the groups' k2_cache (first call of a new length only)
 };
 
 // 0 auto, 1 force the 3-kernel scan path, 2 force the tensor-core kernel whenever its tables exist
@@ -472,7 +478,7 @@ static void matpow(const std::vector<double> &a, int64_t p, std::vector<double> 
 }
 
 template <typename S, int NSEC>
-static int run_group(const SosGroup &g, const S *x, S *y, int64_t n_in, int64_t n_rate, int64_t n_out,
+static int run_group(const SosGroup &g, std::mutex *k2_mutex, const S *x, S *y, int64_t n_in, int64_t n_rate, int64_t n_out,
                      int32_t L, int32_t M, const void *zi, void *zf, unsigned char *ws,
                      cudaStream_t stream)
 {
@@ -518,15 +524,25 @@ static int run_group(const SosGroup &g, const S *x, S *y, int64_t n_in, int64_t 
     k1<<<(unsigned)n_tiles, SOS_NT, smem1, stream>>>(a);
     B200_CHECK_LAUNCH("sos_pass1_kernel");
 
-    // tile-level scan matrices: m1 = A^T, pj = (A^T)^(run*2^j)
+    // tile-level scan matrices: m1 = A^T, pj = (A^T)^(run*2^j) -- from the plan's cache (host matrix powers are
+    // computed once per distinct call length, not per call)
     TileScanMats<D> mm;
     const int64_t run = (n_tiles + SOS_K2_NT - 1) / SOS_K2_NT;
     memcpy(mm.m1, g.tileA.data(), sizeof(double) * D * D);
-    std::vector<double> p;
-    matpow(g.tileA, run, p, D);
-    for (int j = 0; j < SOS_K2_LEVELS; ++j) {
-        memcpy(mm.pj[j], p.data(), sizeof(double) * D * D);
-        if (j + 1 < SOS_K2_LEVELS) matmul(p, p, p, D);
+    {
+        std::lock_guard<std::mutex> lock(*k2_mutex);
+        auto it = g.k2_cache.find(run);
+        if (it == g.k2_cache.end()) {
+            std::vector<double> all((size_t)SOS_K2_LEVELS * D * D), p;
+            matpow(g.tileA, run, p, D);
+            for (int j = 0; j < SOS_K2_LEVELS; ++j) {
+                memcpy(all.data() + (size_t)j * D * D, p.data(), sizeof(double) * D * D);
+                if (j + 1 < SOS_K2_LEVELS) matmul(p, p, p, D);
+            }
+            if (g.k2_cache.size() > 64) g.k2_cache.clear();
+            it = g.k2_cache.emplace(run, std::move(all)).first;
+        }
+        for (int j = 0; j < SOS_K2_LEVELS; ++j) memcpy(mm.pj[j], it->second.data() + (size_t)j * D * D, sizeof(double) * D * D);
     }
     auto k2 = sos_tile_scan_kernel<C, D>;
     size_t smem2 = sizeof(double) * (size_t)D * SOS_K2_NT;
@@ -539,16 +555,16 @@ static int run_group(const SosGroup &g, const S *x, S *y, int64_t n_in, int64_t 
 }
 
 template <typename S>
-static int run_group_nsec(const SosGroup &g, const S *x, S *y, int64_t n_in, int64_t n_rate,
+static int run_group_nsec(const SosGroup &g, std::mutex *k2m, const S *x, S *y, int64_t n_in, int64_t n_rate,
                           int64_t n_out, int32_t L, int32_t M, const void *zi, void *zf,
                           unsigned char *ws, cudaStream_t st)
 {
     switch (g.nsec) {
-    case 1: return run_group<S, 1>(g, x, y, n_in, n_rate, n_out, L, M, zi, zf, ws, st);
-    case 2: return run_group<S, 2>(g, x, y, n_in, n_rate, n_out, L, M, zi, zf, ws, st);
-    case 4: return run_group<S, 4>(g, x, y, n_in, n_rate, n_out, L, M, zi, zf, ws, st);
-    case 6: return run_group<S, 6>(g, x, y, n_in, n_rate, n_out, L, M, zi, zf, ws, st);
-    case 8: return run_group<S, 8>(g, x, y, n_in, n_rate, n_out, L, M, zi, zf, ws, st);
+    case 1: return run_group<S, 1>(g, k2m, x, y, n_in, n_rate, n_out, L, M, zi, zf, ws, st);
+    case 2: return run_group<S, 2>(g, k2m, x, y, n_in, n_rate, n_out, L, M, zi, zf, ws, st);
+    case 4: return run_group<S, 4>(g, k2m, x, y, n_in, n_rate, n_out, L, M, zi, zf, ws, st);
+    case 6: return run_group<S, 6>(g, k2m, x, y, n_in, n_rate, n_out, L, M, zi, zf, ws, st);
+    case 8: return run_group<S, 8>(g, k2m, x, y, n_in, n_rate, n_out, L, M, zi, zf, ws, st);
     }
     set_error("sos: bad group size %d", g.nsec);
     return B200DSP_E_BADARG;
@@ -685,7 +701,7 @@ static int sos_run(const b200dsp_sos_plan_impl *p, const S *x, S *y, int64_t n, 
         S *dst = (last && !(stage && M > 1)) ? y : tmp;
         const C *zig = zi ? static_cast<const C *>(zi) + sec0 * 2 * NCH : nullptr;
         C *zfg = zf ? static_cast<C *>(zf) + sec0 * 2 * NCH : nullptr;
-        int rc = run_group_nsec<S>(g, src, dst, first ? n_in0 : n_rate, n_rate,
+        int rc = run_group_nsec<S>(g, &p->k2_mutex, src, dst, first ? n_in0 : n_rate, n_rate,
                                    (last && M_last > 1) ? n_out : n_rate,
                                    first ? L0 : 1, last ? M_last : 1, zig, zfg, ws, st);
         if (rc != B200DSP_OK) return rc;
@@ -834,6 +850,24 @@ int b200dsp_sos_filter(const b200dsp_sos_plan *plan, int dtype, const void *x, v
     case B200DSP_C128: return sos_run<double2>(plan, (const double2 *)x, (double2 *)y, n, L, M, zi, zf, w, dtype, st);
     }
     return B200DSP_E_DTYPE;
+}
+
+int b200dsp_sos_filter_batch(const b200dsp_sos_plan *plan, int dtype, const void *x, void *y, int64_t rows, int64_t n,
+                             int64_t x_row_stride, int64_t y_row_stride, void *ws, size_t ws_bytes, void *stream)
+{
+    if (!plan || rows < 0 || n < 0 || x_row_stride < n || y_row_stride < n || dtype_size(dtype) == 0) {
+        set_error("sos_filter_batch: bad argument");
+        return B200DSP_E_BADARG;
+    }
+    const size_t es = dtype_size(dtype);
+    for (int64_t r = 0; r < rows && n > 0; ++r) {
+        // rows run one after the other on the stream, so they can share one workspace
+        const int rc = b200dsp_sos_filter(plan, dtype, static_cast<const char *>(x) + (size_t)r * x_row_stride * es,
+                                          static_cast<char *>(y) + (size_t)r * y_row_stride * es, n, 1, 1, nullptr, nullptr,
+                                          ws, ws_bytes, stream);
+        if (rc != B200DSP_OK) return rc;
+    }
+    return B200DSP_OK;
 }
 
 void b200dsp_set_sos_variant(int variant) { g_sos_variant = variant; }

@@ -23,10 +23,10 @@ REAL_OF = {torch.float32: torch.float32, torch.float64: torch.float64,
 SYMBOLS = (
     "b200dsp_version", "b200dsp_last_error", "b200dsp_device_info",
     "b200dsp_fir_plan_create", "b200dsp_fir_plan_destroy", "b200dsp_fir_plan_ntaps",
-    "b200dsp_fir_filter", "b200dsp_fir_up", "b200dsp_fir_up_hist_len", "b200dsp_fir_dn",
+    "b200dsp_fir_filter", "b200dsp_fir_filter_batch", "b200dsp_fir_up", "b200dsp_fir_up_hist_len", "b200dsp_fir_dn",
     "b200dsp_sos_plan_create", "b200dsp_sos_plan_destroy", "b200dsp_sos_plan_nsec",
-    "b200dsp_sos_workspace_bytes", "b200dsp_sos_filter",
-    "b200dsp_upsample", "b200dsp_downsample",
+    "b200dsp_sos_workspace_bytes", "b200dsp_sos_filter", "b200dsp_sos_filter_batch",
+    "b200dsp_upsample", "b200dsp_downsample", "b200dsp_combine_complex",
     "b200dsp_launch_count", "b200dsp_launch_count_reset", "b200dsp_set_fir_variant",
     "b200dsp_set_sos_variant",
 )
@@ -50,6 +50,9 @@ def _load():
     lib.b200dsp_fir_plan_ntaps.argtypes = [P]
     lib.b200dsp_fir_plan_ntaps.restype = I32
     lib.b200dsp_fir_filter.argtypes = [P, I, P, P, P, I64, P]
+    lib.b200dsp_fir_filter_batch.argtypes = [P, I, P, P, I64, I64, I64, I64, P]
+    lib.b200dsp_sos_filter_batch.argtypes = [P, I, P, P, I64, I64, I64, I64, P, SZ, P]
+    lib.b200dsp_combine_complex.argtypes = [I, P, P, P, I64, P]
     lib.b200dsp_fir_up.argtypes = [P, I, P, P, P, I64, I32, P]
     lib.b200dsp_fir_up_hist_len.argtypes = [P, I32]
     lib.b200dsp_fir_up_hist_len.restype = I32

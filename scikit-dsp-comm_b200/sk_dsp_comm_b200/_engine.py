@@ -114,6 +114,58 @@ def fir_filter(plan: FirPlan, x: torch.Tensor, hist=None, out=None) -> torch.Ten
     return y
 
 
+def _check_rows(x: torch.Tensor):
+    if not x.is_cuda:
+        raise ValueError("device-level call needs a CUDA tensor")
+    if x.dtype not in DTYPE_CODE:
+        raise NotImplementedError("input type '%s' not supported" % x.dtype)
+    if x.dim() != 2 or not x.is_contiguous():
+        raise ValueError("batched call needs a contiguous (rows, n) tensor")
+
+
+def fir_filter_batch(plan: FirPlan, x: torch.Tensor) -> torch.Tensor:
+    """Every row of the (rows, n) tensor filtered from zero state: one C call (b200dsp_fir_filter_batch)."""
+    _check_rows(x)
+    dev = _dev_index(x)
+    y = torch.empty_like(x)
+    rows, n = x.shape
+    with torch.cuda.device(dev):
+        check(lib.b200dsp_fir_filter_batch(plan.handle(dev), DTYPE_CODE[x.dtype], x.data_ptr(), y.data_ptr(),
+                                           rows, n, n, n, _cabi.stream_ptr(dev)), "fir_filter_batch")
+    return y
+
+
+def sos_filter_batch(plan: SosPlan, x: torch.Tensor) -> torch.Tensor:
+    """Every row of the (rows, n) tensor through the cascade from zero state: one C call."""
+    _check_rows(x)
+    dev = _dev_index(x)
+    y = torch.empty_like(x)
+    rows, n = x.shape
+    if rows and n:
+        code = DTYPE_CODE[x.dtype]
+        with torch.cuda.device(dev):
+            h = plan.handle(dev)
+            nbytes = int(lib.b200dsp_sos_workspace_bytes(h, code, n, 1, 1))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+            check(lib.b200dsp_sos_filter_batch(h, code, x.data_ptr(), y.data_ptr(), rows, n, n, n, ws.data_ptr(),
+                                               nbytes, _cabi.stream_ptr(dev)), "sos_filter_batch")
+    return y
+
+
+def combine_complex(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a + 1j*b on the device (b200dsp_combine_complex): real a, b -> complex; complex a, b -> complex."""
+    _check_x(a)
+    if b.dtype != a.dtype or b.shape != a.shape or not b.is_cuda or not b.is_contiguous():
+        raise ValueError("combine_complex needs two matching contiguous CUDA tensors")
+    dev = _dev_index(a)
+    odt = {torch.float32: torch.complex64, torch.float64: torch.complex128}.get(a.dtype, a.dtype)
+    y = torch.empty(a.numel(), dtype=odt, device=a.device)
+    with torch.cuda.device(dev):
+        check(lib.b200dsp_combine_complex(DTYPE_CODE[a.dtype], a.data_ptr(), b.data_ptr(), y.data_ptr(), a.numel(),
+                                          _cabi.stream_ptr(dev)), "combine_complex")
+    return y
+
+
 def fir_up(plan: FirPlan, x: torch.Tensor, L: int, hist=None, out=None) -> torch.Tensor:
     _check_x(x)
     dev = _dev_index(x)

@@ -147,9 +147,23 @@ class multirate_FIR(object):
         if barr.ndim != 1 or barr.size == 0:
             # scipy.signal.lfilter: "object of too small depth" / empty numerator
             raise ValueError("numerator b must be a non-empty 1-D sequence of taps")
+        # complex taps (scipy.signal.lfilter accepts them, multirate_helper.py:108): by linearity two real-tap
+        # passes, y = FIR(b.real, x) + 1j * FIR(b.imag, x), combined on the device (b200dsp_combine_complex)
+        self._plan_im = None
         if barr.dtype.kind == "c":
-            raise NotImplementedError("complex FIR taps are not supported by the B200 engine")
-        self._plan = _engine.FirPlan(barr.astype(np.float64))
+            self._plan = _engine.FirPlan(np.ascontiguousarray(barr.real, dtype=np.float64))
+            self._plan_im = _engine.FirPlan(np.ascontiguousarray(barr.imag, dtype=np.float64))
+        else:
+            self._plan = _engine.FirPlan(barr.astype(np.float64))
+
+    def _both(self, run, t):
+        """run(plan, tensor) for the real-tap plan, and the imaginary-tap plan when the taps are complex."""
+        yr = run(self._plan, t)
+        if self._plan_im is None:
+            return yr
+        yi = run(self._plan_im, t)
+        shape = yr.shape
+        return _engine.combine_complex(yr.reshape(-1).contiguous(), yi.reshape(-1).contiguous()).reshape(shape)
 
     # -- reference: y = signal.lfilter(self.b,[1],x)  (multirate_helper.py:104-109)
     def filter(self, x, zi=None):
@@ -162,14 +176,21 @@ class multirate_FIR(object):
         """
         if zi is not None:
             return self._filter_stateful(x, zi)
-        if isinstance(x, torch.Tensor) and not x.is_cuda and x.dim() == 1 \
+        if isinstance(x, torch.Tensor) and not x.is_cuda and x.dim() == 1 and self._plan_im is None \
                 and x.numel() >= _HOST_PIPE_MIN and x.dtype in _engine.DTYPE_CODE:
             from . import hostpipe
             return hostpipe.fir_filter_host(self._plan, x)
         st = Staged(x)
-        rows, shape = _rows(st.tensor)
-        outs = [_engine.fir_filter(self._plan, r) if r.numel() else r.clone() for r in rows]
-        y = outs[0] if shape is None else torch.stack(outs).reshape(shape)
+        t = st.tensor
+        if t.numel() == 0:
+            y = t.clone() if self._plan_im is None or t.is_complex() else \
+                t.to(torch.complex64 if t.dtype == torch.float32 else torch.complex128)
+        elif t.dim() == 1:
+            y = self._both(_engine.fir_filter, t.contiguous())
+        else:
+            # lfilter filters the last axis of an N-D array: all rows in one C call
+            flat = t.reshape(-1, t.shape[-1]).contiguous()
+            y = self._both(_engine.fir_filter_batch, flat).reshape(t.shape)
         return st.finish(y)
 
     def _filter_stateful(self, x, zi):
@@ -180,6 +201,8 @@ class multirate_FIR(object):
         the block and that (K-1)-sample launch run on the device; nothing is read back, so a stream of
         blocks chained through ``zf`` never synchronises with the host."""
         _require_1d(x, "filter(zi=...)")
+        if self._plan_im is not None:
+            raise NotImplementedError("filter(zi=...) with complex taps is not supported by the B200 engine")
         K = self._plan.ntaps
         st = Staged(x)
         t = st.tensor.contiguous()
@@ -226,7 +249,7 @@ class multirate_FIR(object):
         t = st.tensor.contiguous()
         if t.numel() == 0:
             return st.finish(t.clone())
-        y = _engine.fir_up(self._plan, t, L)
+        y = self._both(lambda pl, tt: _engine.fir_up(pl, tt, L), t)
         if L != L_change:
             y = y * (float(L_change) / L)     # reference gain is the un-truncated L_change
         return st.finish(y)
@@ -243,7 +266,7 @@ class multirate_FIR(object):
         t = st.tensor.contiguous()
         if t.numel() // M_change == 0:
             return st.finish(torch.empty(0, dtype=t.dtype, device=t.device))
-        return st.finish(_engine.fir_dn(self._plan, t, M_change))
+        return st.finish(self._both(lambda pl, tt: _engine.fir_dn(pl, tt, M_change), t))
 
     def freq_resp(self, mode='dB', fs=8000, ylim=[-100, 2]):
         raise NotImplementedError("plot helpers are out of scope of the B200 engine (SURVEY.md section 2)")
@@ -330,9 +353,12 @@ class multirate_IIR(object):
                 return st.finish(y), zf.cpu().numpy()
             return st.finish(y), (zf if st.kind == "cuda" else zf.cpu())
         st = Staged(x)
-        rows, shape = _rows(st.tensor)
-        outs = [_engine.sos_filter(plan, r) for r in rows]
-        y = outs[0] if shape is None else torch.stack(outs).reshape(shape)
+        t = st.tensor
+        if t.dim() == 1:
+            y = _engine.sos_filter(plan, t.contiguous())
+        else:
+            # sosfilt filters the last axis of an N-D array: all rows in one C call
+            y = _engine.sos_filter_batch(plan, t.reshape(-1, t.shape[-1]).contiguous()).reshape(t.shape)
         return st.finish(y)
 
     # -- reference: y = L*upsample(x,L); y = sosfilt(sos,y)  (multirate_helper.py:177-183)

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), "missing export: " + s
     assert sorted(cabi.SYMBOLS) == syms
-    assert lib.b200dsp_version() == 100
+    assert lib.b200dsp_version() == 200
 
 
 def test_library_is_sm100a_native():
