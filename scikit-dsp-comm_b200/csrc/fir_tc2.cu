@@ -14,16 +14,16 @@
 //           descriptor simply starts 128*j bytes later in the SAME stream (one swizzle row = 64 fp16)
 //       D (TMEM accumulators, fp32): lanes = (c, part), columns = r  ->  y[t0 + 64 r + c]
 //
-// One MMA (M=128,N=64,K=16) now reads 2 KB from shared memory instead of 6 KB and produces both the
-// b_hi*x and b_lo*x products.  Per complex sample: 2 channels x 2 sample parts (x_hi, x_lo) x 20 k-slices.
-//   y = (hh + 2^-11 (lh + hl)) / (s_x s_b),  hh = b_hi*x_hi, lh = b_lo*x_hi, hl = b_hi*x_lo (ll dropped).
+// One MMA (M=128, N=96, K=16) reads 3 KB from shared memory and produces both the b_hi*x and b_lo*x products.
+// Per complex sample: 2 channels x 2 sample parts (x_lo first, then x_hi) x 20 k-slices = 80 MMAs per 96-row tile;
+// all four partial products are accumulated (the epilogue adds the hi and lo lanes): y = D / (s_x s_b).
 //
-// Data movement: a producer thread streams raw complex64 tiles (34 KB) into a 6-deep shared-memory
-// ring with 1-D bulk TMA (cp.async.bulk + mbarrier complete_tx); converter warps turn a stage IN PLACE
-// into four swizzled fp16 streams (re/im x hi/lo) around a per-tile power-of-two scale; the MMA thread
-// consumes it; tcgen05.commit recycles the stage.  Accumulators are double buffered per channel so the
-// epilogue (TMEM -> registers -> shuffle-combine hi/lo lanes -> coalesced complex64 stores) overlaps
-// the next channel's MMAs.
+// Data movement: a producer warp streams raw complex64 tiles (51 KB for 96 rows) into a 4-deep shared-memory
+// ring with 1-D bulk TMA (cp.async.bulk + mbarrier complete_tx); 8 converter warps turn a stage IN PLACE
+// into four swizzled fp16 streams (re/im x hi/lo) around a per-tile power-of-two scale; one elected lane of the
+// MMA warp consumes it; tcgen05.commit recycles the stage.  A ring of three accumulators lets two epilogue
+// warpgroups (TMEM -> registers -> shuffle-combine hi/lo lanes -> coalesced complex64 stores) overlap the next
+// channel's MMAs.  Tile heights 64 / 80 / 128 are kept as tuning variants.
 #include "tc_common.cuh"
 
 namespace b200dsp {

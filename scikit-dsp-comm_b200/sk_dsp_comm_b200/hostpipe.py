@@ -3,8 +3,10 @@
 This is what ``multirate_FIR.filter`` runs when it is handed a long HOST array (a torch CPU
 tensor, ideally pinned): the stream is cut into chunks, every chunk carries the previous
 ``ntaps-1`` samples as its overlap-save halo (``hist`` argument of ``b200dsp_fir_filter``), and
-copies of chunk i+1 / i-1 overlap the kernel of chunk i.  The result is bit-identical to the
-monolithic device call because the halo reproduces the filter state exactly.
+copies of chunk i+1 / i-1 overlap the kernel of chunk i.  The halo reproduces the filter state
+exactly: for float64 / complex128 the result is bit-identical to the monolithic device call; the
+float32 / complex64 tensor-core kernels anchor their tile grid (block scales, summation order) at each
+launch's first sample, so there a different cut changes the last bits (both within 1e-6 max|y| of the oracle).
 
 bench.py's ``e2e`` number is measured through this path (host buffers in, host buffers out).
 """
@@ -65,15 +67,21 @@ class _Pipe:
         self.s_d2h = torch.cuda.Stream(dev)
 
 
-_pipes = {}
+_pipes = {}          # insertion-ordered: least recently used first
+_MAX_PIPES = 4       # bounded: each pipe owns 6 device buffers of ~chunk samples
 
 
 def _pipe(dev, dtype, chunk, k1):
-    key = (dev.index, dtype, chunk, k1)
-    p = _pipes.get(key)
+    """Staging buffers are keyed on a chunk size rounded up to a power of two (callers slice what they need), and
+    the cache is a small LRU: streams of varying length no longer grow device memory without bound."""
+    cap = 1 << max(int(chunk - 1).bit_length(), 10)
+    key = (dev.index, dtype, cap, k1)
+    p = _pipes.pop(key, None)
     if p is None:
-        p = _Pipe(dev, dtype, chunk, k1)
-        _pipes[key] = p
+        while len(_pipes) >= _MAX_PIPES:
+            _pipes.pop(next(iter(_pipes)))          # drop the least recently used set of buffers
+        p = _Pipe(dev, dtype, cap, k1)
+    _pipes[key] = p
     return p
 
 
