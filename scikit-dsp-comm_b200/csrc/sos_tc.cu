@@ -73,16 +73,24 @@ constexpr int SOP_BYTES = NCHUNK * 128;       // chunk start states as an MMA op
 // shared memory map (offsets from the 1024-aligned base)
 constexpr int SM_RAW = NSTAGE * STAGE_BYTES;                  // [NRAW][STAGE_BYTES]      raw fp32 tiles
 constexpr int SM_SOP = SM_RAW + NRAW * STAGE_BYTES;           // [2][SOP_BYTES]           K-major SWIZZLE_128B, 1024-aligned
-constexpr int SM_SMAT = SM_SOP + 2 * SOP_BYTES;               // double [7][16*16]
-constexpr int SM_FOLD = SM_SMAT + NSMAT * 256 * 8;            // float [18][FOLD_PITCH]
-constexpr int SM_ESM = SM_FOLD + NFOLD * FOLD_PITCH * 4;      // float [2][64][EP]   carries (warp 8 -> scan warp b), overwritten in
-                                                              //                     place by the zero-state start states (-> chain)
-constexpr int SM_AGG = SM_ESM + 2 * NCHUNK * EP * 4;          // double [2][16]           zero-state end state of a tile
-constexpr int SM_BAR = SM_AGG + 2 * 16 * 8;
-constexpr int NBAR = 2 * NRAW + 2 * NSTAGE + 9 * NACC;
-constexpr int SM_MISC = SM_BAR + NBAR * 8;                    // tmem slot, wmax[4], tile_e[16], tile_m[16]
-constexpr int SMEM_TOTAL = SM_MISC + 256 + 1024;
-static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
+// the rest depends on the in-tile scan type: float64 scans (Z64) need all seven float64 matrices and a 2-deep ring
+// of carry buffers; float32 scans need only A^8192 in float64 (chain) but 18 float32 matrices, and get a 4-deep
+// ring of carry buffers so that the scan warps never wait for the chain warp to hand a buffer back
+template <bool Z64> struct Lay {
+    static constexpr int ESM_DEPTH = Z64 ? 2 : 4;
+    static constexpr int NSMAT_SM = Z64 ? NSMAT : 1;              // float32 scans: slot 0 = A^8192
+    static constexpr int NFOLD_SM = Z64 ? 13 : NFOLD;
+    static constexpr int SM_SMAT = SM_SOP + 2 * SOP_BYTES;        // double [NSMAT_SM][16*16]
+    static constexpr int SM_FOLD = SM_SMAT + NSMAT_SM * 256 * 8;  // float [NFOLD_SM][FOLD_PITCH]
+    static constexpr int SM_ESM = SM_FOLD + NFOLD_SM * FOLD_PITCH * 4;   // float [ESM_DEPTH][64][EP]  carries (warp 8 -> scan
+                                                                  // warp), overwritten in place by the zero-state start states
+    static constexpr int SM_AGG = SM_ESM + ESM_DEPTH * NCHUNK * EP * 4;  // double [ESM_DEPTH][16]  zero-state end state of a tile
+    static constexpr int SM_BAR = SM_AGG + ESM_DEPTH * 16 * 8;
+    static constexpr int NBAR = 2 * NRAW + 2 * NSTAGE + 6 * NACC + 3 * ESM_DEPTH;
+    static constexpr int SM_MISC = SM_BAR + NBAR * 8;             // tmem slot, wmax[2][4], tile_e[16], tile_m[16]
+    static constexpr int SMEM_TOTAL = SM_MISC + 256 + 1024;
+    static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
+};
 
 struct Args {
     const float *x;
@@ -201,6 +209,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
     unsigned char *sm = smem_dyn + (base - raw_base);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
+    using LY = Lay<Z64>;
+    constexpr int ESM_DEPTH = LY::ESM_DEPTH;
+    constexpr int SM_SMAT = LY::SM_SMAT, SM_FOLD = LY::SM_FOLD, SM_ESM = LY::SM_ESM, SM_AGG = LY::SM_AGG,
+                  SM_BAR = LY::SM_BAR, SM_MISC = LY::SM_MISC;
     const uint32_t bar0 = base + SM_BAR;
     constexpr int B0 = 2 * NRAW + 2 * NSTAGE;
     auto RAW_FULL = [&](int r) { return bar0 + 8u * r; };
@@ -213,9 +225,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
     auto D_EMPTY = [&](int b) { return bar0 + 8u * (B0 + 3 * NACC + b); };
     auto S_READY = [&](int b) { return bar0 + 8u * (B0 + 4 * NACC + b); };
     auto SOP_EMPTY = [&](int b) { return bar0 + 8u * (B0 + 5 * NACC + b); };
-    auto Z_READY = [&](int b) { return bar0 + 8u * (B0 + 6 * NACC + b); };
-    auto ESM_READY = [&](int b) { return bar0 + 8u * (B0 + 7 * NACC + b); };
-    auto ESM_EMPTY = [&](int b) { return bar0 + 8u * (B0 + 8 * NACC + b); };
+    // carry-buffer ring (ESM_DEPTH deep): indexed by tile % ESM_DEPTH
+    auto Z_READY = [&](int e) { return bar0 + 8u * (B0 + 6 * NACC + e); };
+    auto ESM_READY = [&](int e) { return bar0 + 8u * (B0 + 6 * NACC + ESM_DEPTH + e); };
+    auto ESM_EMPTY = [&](int e) { return bar0 + 8u * (B0 + 6 * NACC + 2 * ESM_DEPTH + e); };
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + SM_MISC);
     float *wmax = reinterpret_cast<float *>(sm + SM_MISC + 16);
     int *tile_e = reinterpret_cast<int *>(sm + SM_MISC + 48);                    // wmax: [2][4] floats
@@ -241,17 +254,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
             mbar_init(D_EMPTY(b), N_EPI_WARPS);
             mbar_init(S_READY(b), 1);
             mbar_init(SOP_EMPTY(b), 1);
-            mbar_init(Z_READY(b), 1);
-            mbar_init(ESM_READY(b), 1);
-            mbar_init(ESM_EMPTY(b), 1);
+        }
+        for (int e = 0; e < ESM_DEPTH; ++e) {
+            mbar_init(Z_READY(e), 1);
+            mbar_init(ESM_READY(e), 1);
+            mbar_init(ESM_EMPTY(e), 1);
         }
         fence_barrier_init();
     }
     if (tid < E_RING) tile_m[tid] = 0.f;
     // the correction operand rows hold 32 of 64 fp16: clear the rest once (0 * garbage could be NaN)
     for (int i = tid; i < 2 * SOP_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4 *>(sm + SM_SOP)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < NSMAT * ND * ND; i += NTHREADS) smat[i] = a.smat[i];
-    for (int i = tid; i < NFOLD * FOLD_PITCH; i += NTHREADS) fold[i] = a.fold[i];
+    // float64 scans: all seven matrices; float32 scans: only A^8192 (slot 6 of the plan's table -> slot 0 here)
+    for (int i = tid; i < LY::NSMAT_SM * ND * ND; i += NTHREADS) smat[i] = a.smat[(Z64 ? 0 : 6 * ND * ND) + i];
+    for (int i = tid; i < LY::NFOLD_SM * FOLD_PITCH; i += NTHREADS) fold[i] = a.fold[i];
     if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), 512);
     tc_fence_before();
     __syncthreads();
@@ -408,10 +424,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
         auto eread = [&](int eit) {
             const int eb = eit & 1;
             const uint32_t epb = (uint32_t)(eit >> 1) & 1u;
-            STC_WAIT(ESM_EMPTY(eb), epb ^ 1u, 13);
+            const int ee = eit % ESM_DEPTH;
+            STC_WAIT(ESM_EMPTY(ee), ((uint32_t)(eit / ESM_DEPTH) & 1u) ^ 1u, 13);
             STC_WAIT(E_FULL(eb), epb, 14);
             tc_fence_after();
-            float *es = esm + eb * NCHUNK * EP;
+            float *es = esm + ee * NCHUNK * EP;
             const float sc = ldexpf(rowinv, -tile_e[eit % E_RING]);
             const uint32_t eaddr = tmem_base + ACC_COL0 + eb * ACC_STRIDE + NCHUNK;     // TMEM lanes 0..31
 #pragma unroll 1
@@ -431,7 +448,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(E_EMPTY(eb));
-                mbar_arrive(ESM_READY(eb));
+                mbar_arrive(ESM_READY(ee));
             }
             __syncwarp();
         };
@@ -496,11 +513,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
         int mstride;
         if constexpr (Z64) { MA128 = smat; MKS = smat + ND * ND; mstride = ND * ND; }
         else { MA128 = fold + 12 * FOLD_PITCH; MKS = fold + 13 * FOLD_PITCH; mstride = FOLD_PITCH; }
-        float *es = esm + b * NCHUNK * EP;
         int it = b;
         for (int64_t tile = t_begin + b; tile < t_end; tile += 2, it += 2) {
-            const uint32_t pb = (uint32_t)(it >> 1) & 1u;
-            STC_WAIT(ESM_READY(b), pb, 5);
+            const int ee = it % ESM_DEPTH;
+            const uint32_t pe = (uint32_t)(it / ESM_DEPTH) & 1u;
+            float *es = esm + ee * NCHUNK * EP;
+            STC_WAIT(ESM_READY(ee), pe, 5);
             // lane l owns chunks 2l, 2l+1
             ZT q[ND], o[ND], zs[ND];
             const float *e0 = es + (2 * lane) * EP, *e1 = e0 + EP;
@@ -536,7 +554,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
                     }
                     if (lane == 31) {
 #pragma unroll
-                        for (int k = 0; k < ND; ++k) aggsm[b * 16 + k] = (double)q[k];
+                        for (int k = 0; k < ND; ++k) aggsm[ee * 16 + k] = (double)q[k];
                     }
 #pragma unroll
                     for (int k = 0; k < ND; k += 4) {
@@ -558,7 +576,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(Z_READY(b));
+            if (lane == 0) mbar_arrive(Z_READY(ee));
         }
     } else if (warp == CHAIN_WARP) {
         // =============================== serial chain between tiles ===============================
@@ -572,7 +590,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
             s_in[k] = (blockIdx.x == 0 && a.zi != nullptr && k < a.d_real) ? (double)a.zi[k] : 0.0;
         const float *Ph = fold + (lane >> 2) * FOLD_PITCH, *Qm = fold + (8 + (lane & 3)) * FOLD_PITCH;
         const float *F128 = fold + 12 * FOLD_PITCH;
-        const double *MAT = smat + 6 * ND * ND;            // A^8192
+        const double *MAT = smat + (Z64 ? 6 : 0) * ND * ND;            // A^8192
         int it = 0;
         for (int64_t tile = t_begin; tile < t_end; ++tile, ++it) {
             const int b = it & 1;
@@ -589,12 +607,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
                 mv_f32<ND>(h1, Mt, h0);
             }
             // now h1 = chunk 2l+1's share, h0 = chunk 2l's share (the input of the last pass)
-            STC_WAIT(Z_READY(b), pb, 8);
+            const int ee = it % ESM_DEPTH;
+            STC_WAIT(Z_READY(ee), (uint32_t)(it / ESM_DEPTH) & 1u, 8);
             double nxt[ND];
 #pragma unroll
-            for (int k = 0; k < ND; ++k) nxt[k] = aggsm[b * 16 + k];
+            for (int k = 0; k < ND; ++k) nxt[k] = aggsm[ee * 16 + k];
             if (!a.at_zero) mv_acc<ND>(nxt, MAT, s_in);
-            const float *d0 = esm + (b * NCHUNK + 2 * lane) * EP, *d1 = d0 + EP;
+            const float *d0 = esm + (ee * NCHUNK + 2 * lane) * EP, *d1 = d0 + EP;
 #pragma unroll
             for (int k = 0; k < ND; k += 4) {
                 const float4 z0 = *reinterpret_cast<const float4 *>(d0 + k), z1 = *reinterpret_cast<const float4 *>(d1 + k);
@@ -602,7 +621,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sos_tc_kernel(const Args a)
                 h1[k] += z1.x; h1[k + 1] += z1.y; h1[k + 2] += z1.z; h1[k + 3] += z1.w;     //                     chunk 2l+1
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(ESM_EMPTY(b));            // carries / start states / aggregate of this buffer consumed
+            if (lane == 0) mbar_arrive(ESM_EMPTY(ee));           // carries / start states / aggregate of this buffer consumed
             // the two chunk rows of the correction operand: fp16 hi (k 0..15) and residual (k 16..31) of s_d * sfac[d] * 2^e_x
             STC_WAIT(SOP_EMPTY(b), pb ^ 1u, 17);
             {
@@ -1153,8 +1172,9 @@ int launch_sos_tc(const StcTables &t, const float *x, float *y, int64_t n_in, in
     {                                                                                    \
         auto kern = a.dbg ? (z64 ? sos_tc_kernel<NDV, true, true> : sos_tc_kernel<NDV, false, true>)      \
                           : (z64 ? sos_tc_kernel<NDV, true, false> : sos_tc_kernel<NDV, false, false>);   \
-        B200_CHECK_CUDA(allow_smem(kern, SMEM_TOTAL));                                   \
-        kern<<<(unsigned)nblk, NTHREADS, SMEM_TOTAL, stream>>>(a);                       \
+        const int smem_total = z64 ? Lay<true>::SMEM_TOTAL : Lay<false>::SMEM_TOTAL;     \
+        B200_CHECK_CUDA(allow_smem(kern, smem_total));                                   \
+        kern<<<(unsigned)nblk, NTHREADS, smem_total, stream>>>(a);                       \
     }
     switch (t.nd) {
     case 4: STC_LAUNCH(4) break;
