@@ -265,6 +265,7 @@ struct b200dsp_fir_plan_impl {
     int32_t tcr_sb[4][5];
     int8_t tcr_state[4][5];   // 1 ready, otherwise this (mode, factor) does not fit the tensor-core kernel
     void *tcr_pool;           // one allocation for all of them (plan_create)
+    void *fft_tables;         // fir_fft.cu: digit-reversed spectrum of the taps + twiddles (2 <= ntaps <= 2049), or NULL
     int32_t sm_count;
 };
 
@@ -273,6 +274,10 @@ int tcr_build(const double *taps, int ntaps, int mode, int P, unsigned char *out
 int tcr_matrix_bytes(int mode, int P);
 int launch_fir_tc_real(int mode, int P, const void *x, const void *hist, void *y, int64_t n, int32_t hist_len,
                        const void *amat_dev, int sb_exp, int ntaps, int sm_count, cudaStream_t stream);
+// fir_fft.cu
+int fft_build_tables(const double *taps, int ntaps, float *out);
+int launch_fir_fft(const void *x, const void *hist, void *y, int64_t n, int32_t hist_len, const void *tables_dev,
+                   int ntaps, cudaStream_t stream);
 // fir_tc2.cu
 int tc2_build_tap_matrix(const double *taps, int ntaps, unsigned char *out, int *sb_exp);
 int tc2_matrix_bytes();
@@ -503,6 +508,10 @@ static int fir_dispatch(const b200dsp_fir_plan_impl *p, int dtype, const void *x
                 return launch_fir_tc2(x, hist, y, n, hist_len, p->tc2_amat, p->tc2_sb_exp, p->ntaps,
                                       v == 13 ? 128 : (v == 12 ? 64 : (v == 15 ? 80 : 96)), p->sm_count, s);
         }
+        // Longer filters (257 .. 2049 taps): overlap-save with the in-shared-memory 4096-point FFT (fir_fft.cu);
+        // v == 16 forces it for any filter it can take
+        if (L == 1 && M == 1 && p->fft_tables != nullptr && (v == 16 || (v == 0 && p->ntaps > 256 && n >= 32768)))
+            return launch_fir_fft(x, hist, y, n, hist_len, p->fft_tables, p->ntaps, s);
         if (L > 1 && v != 8 && v != 9) {
             const int rc = launch_fir_up_short<float2, 8, true>(p, x, hist, y, n, L, hist_len, s);
             if (rc != B200DSP_E_UNSUPPORTED) return rc;
@@ -579,6 +588,15 @@ int b200dsp_fir_plan_create(const double *taps_host, int32_t ntaps, b200dsp_fir_
         }
         delete[] h2;
     }
+    // overlap-save FFT tables (complex64 streams, 2 .. 2049 taps)
+    p->fft_tables = nullptr;
+    if (e == cudaSuccess && ntaps >= 2 && ntaps <= 2049) {
+        std::vector<float> tb((size_t)4 * 4096);
+        if (fft_build_tables(taps_host, ntaps, tb.data()) == 0) {
+            e = cudaMalloc(&p->fft_tables, tb.size() * sizeof(float));
+            if (e == cudaSuccess) e = cudaMemcpy(p->fft_tables, tb.data(), tb.size() * sizeof(float), cudaMemcpyHostToDevice);
+        }
+    }
     // float32 tensor-core tap matrices: mode 1 filter, 2 up(P), 3 dn(P), P = 2..4 -- every one that fits the filter
     p->tcr_pool = nullptr;
     if (e == cudaSuccess) {
@@ -617,6 +635,7 @@ int b200dsp_fir_plan_create(const double *taps_host, int32_t ntaps, b200dsp_fir_
         cudaFree(p->taps_f64);
         cudaFree(p->tc2_amat);
         cudaFree(p->tcr_pool);
+        cudaFree(p->fft_tables);
         delete[] p->taps_host;
         delete p;
         return B200DSP_E_CUDA;
@@ -632,6 +651,7 @@ void b200dsp_fir_plan_destroy(b200dsp_fir_plan *plan)
     cudaFree(plan->taps_f64);
     cudaFree(plan->tc2_amat);
     cudaFree(plan->tcr_pool);
+    cudaFree(plan->fft_tables);
     delete[] plan->taps_host;
     delete plan;
 }

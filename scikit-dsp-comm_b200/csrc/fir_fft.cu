@@ -1,0 +1,260 @@
+// fir_fft.cu -- complex64 FIR by overlap-save with a hand-written 4096-point FFT held in shared memory.
+//
+// For filters longer than the 256 taps the block-Toeplitz tensor-core kernel takes, a direct form costs O(K) per
+// sample; overlap-save costs O(log N).  This is the engine behind the reference's FFT block filters
+// sigsys.os_filter / oa_filter (src/sk_dsp_comm/sigsys.py:482-598), which compute the same causal FIR
+// y = lfilter(h, 1, x) through N-point FFT frames, and behind multirate_FIR.filter
+// (src/sk_dsp_comm/multirate_helper.py:104-109) for long complex64 filters.
+//
+// One CTA (256 threads) per frame: 4096 input samples starting K-1 before the frame's first output, 4096-(K-1)
+// valid outputs.  4096 = 16 x 16 x 16: three radix-16 passes, every thread computing one 16-point DFT in registers
+// per pass.  Forward = decimation in frequency (natural order in, digit-reversed out); the spectrum of the taps is
+// stored in the SAME digit-reversed order (and pre-scaled by 1/4096), so the product needs no reordering; inverse =
+// decimation in time (digit-reversed in, natural order out).  The last forward pass, the product and the first
+// inverse pass work on the same 16 values of a thread, so a frame needs only four shared-memory exchanges.
+// Shared-memory index p -> p + (p >> 4) (one pad word per 16) makes all three access patterns conflict free.
+// No cuFFT: the transform, the twiddle tables and the frame logic are all here.
+#include "common.cuh"
+#include <math.h>
+#include <vector>
+
+namespace b200dsp {
+namespace fft {
+
+constexpr int N = 4096;
+constexpr int NT = 256;
+constexpr int SM_FLOATS = N + N / 16;              // padded length of one component array
+
+struct Args {
+    const float2 *x;
+    const float2 *hist;
+    float2 *y;
+    const float2 *H;          // [4096] spectrum of the taps / 4096, digit-reversed order
+    const float2 *tw;         // [4096] exp(-2 pi i j / 4096)
+    int64_t n;
+    int32_t hist_len;
+    int32_t ntaps;
+    int32_t valid;            // outputs per frame = 4096 - (ntaps - 1)
+};
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 cmulc(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }   // a * conj(b)
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+// 4-point DFT in place: (a,b,c,d) -> (y0,y1,y2,y3), forward kernel exp(-2 pi i nk/4) (INV: conjugate)
+template <bool INV>
+__device__ __forceinline__ void fft4(float2 &a, float2 &b, float2 &c, float2 &d)
+{
+    const float2 s0 = cadd(a, c), d0 = csub(a, c), s1 = cadd(b, d), d1 = csub(b, d);
+    // forward: -i * d1 = (d1.y, -d1.x); inverse: +i * d1 = (-d1.y, d1.x)
+    const float2 jd = INV ? make_float2(-d1.y, d1.x) : make_float2(d1.y, -d1.x);
+    a = cadd(s0, s1);
+    c = csub(s0, s1);
+    b = cadd(d0, jd);
+    d = csub(d0, jd);
+}
+
+// 16-point DFT of v[0..15] in place; output X[k] ends up in v[4 (k & 3) + (k >> 2)]
+template <bool INV>
+__device__ __forceinline__ void fft16(float2 (&v)[16])
+{
+#pragma unroll
+    for (int j = 0; j < 4; ++j) fft4<INV>(v[j], v[j + 4], v[j + 8], v[j + 12]);
+    // twiddles W16^(j q), q = row index after the first stage (v[j + 4 q])
+    constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, R2 = 0.70710678118654752f;
+    const float2 w1 = make_float2(C1, INV ? S1 : -S1), w2 = make_float2(R2, INV ? R2 : -R2), w3 = make_float2(S1, INV ? C1 : -C1);
+    const float2 w6 = make_float2(-R2, INV ? R2 : -R2), w9 = make_float2(-C1, INV ? -S1 : S1);
+    const float2 w4 = make_float2(0.f, INV ? 1.f : -1.f);
+    v[1 + 4] = cmul(v[1 + 4], w1);  v[2 + 4] = cmul(v[2 + 4], w2);  v[3 + 4] = cmul(v[3 + 4], w3);      // q = 1: j q = 1,2,3
+    v[1 + 8] = cmul(v[1 + 8], w2);  v[2 + 8] = cmul(v[2 + 8], w4);  v[3 + 8] = cmul(v[3 + 8], w6);      // q = 2: 2,4,6
+    v[1 + 12] = cmul(v[1 + 12], w3); v[2 + 12] = cmul(v[2 + 12], w6); v[3 + 12] = cmul(v[3 + 12], w9);  // q = 3: 3,6,9
+#pragma unroll
+    for (int q = 0; q < 4; ++q) fft4<INV>(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+// position of output k of fft16 inside v
+__device__ __forceinline__ constexpr int o16(int k) { return 4 * (k & 3) + (k >> 2); }
+
+__device__ __forceinline__ int pad(int p) { return p + (p >> 4); }
+
+__device__ __forceinline__ float2 load_sample(const Args &a, int64_t g)
+{
+    if (g >= 0) return (g < a.n) ? a.x[g] : make_float2(0.f, 0.f);
+    if (a.hist != nullptr) {
+        const int64_t h = (int64_t)a.hist_len + g;
+        if (h >= 0) return a.hist[h];
+    }
+    return make_float2(0.f, 0.f);
+}
+
+__global__ void __launch_bounds__(NT, 3) fir_fft_os_kernel(const Args a)
+{
+    __shared__ float2 sm[SM_FLOATS];                 // (re, im) pairs: 64-bit accesses, conflict free per half-warp
+    const int t = threadIdx.x;
+    const int64_t out0 = (int64_t)blockIdx.x * a.valid;            // first output of this frame
+    const int64_t g0 = out0 - (a.ntaps - 1);                       // first input sample of the frame
+    float2 v[16];
+
+    // ---- forward pass 1 (over n2, stride 256): inputs straight from global memory (coalesced over t)
+    const bool interior = g0 >= 0 && g0 + N <= a.n;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = interior ? a.x[g0 + t + 256 * j] : load_sample(a, g0 + t + 256 * j);
+    fft16<false>(v);
+    {
+        // W_4096^(k0 t), k0 = 4a + b, as W^(4a t) W^(b t): six table loads, one product deep
+        float2 wb[4], wa[4];
+        wb[0] = wa[0] = make_float2(1.f, 0.f);
+#pragma unroll
+        for (int i = 1; i < 4; ++i) { wb[i] = a.tw[i * t]; wa[i] = a.tw[4 * i * t]; }
+#pragma unroll
+        for (int k0 = 0; k0 < 16; ++k0) {
+            const float2 w = ((k0 & 3) == 0) ? wa[k0 >> 2] : ((k0 >> 2) == 0 ? wb[k0 & 3] : cmul(wa[k0 >> 2], wb[k0 & 3]));
+            const float2 r = (k0 == 0) ? v[o16(0)] : cmul(v[o16(k0)], w);
+            sm[pad(k0 * 256 + t)] = r;
+        }
+    }
+    __syncthreads();
+    // ---- forward pass 2 (over n1, stride 16) inside block k0
+    {
+        const int k0 = t >> 4, n0 = t & 15;
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) {
+            const int p = pad(k0 * 256 + n1 * 16 + n0);
+            v[n1] = sm[p];
+        }
+        fft16<false>(v);
+#pragma unroll
+        for (int k1 = 0; k1 < 16; ++k1) {          // (a thread rewrites exactly the 16 positions it read: no barrier)
+            const float2 w = a.tw[16 * k1 * n0];                   // W_256^(k1 n0)
+            const float2 r = (k1 == 0) ? v[o16(0)] : cmul(v[o16(k1)], w);
+            const int p = pad(k0 * 256 + k1 * 16 + n0);
+            sm[p] = r;
+        }
+    }
+    __syncthreads();
+    // ---- forward pass 3 (over n0), spectrum product, inverse pass 1 (over k2): all on the same 16 values
+    {
+        float2 u[16];
+#pragma unroll
+        for (int n0 = 0; n0 < 16; ++n0) {
+            const int p = pad(t * 16 + n0);
+            v[n0] = sm[p];
+        }
+        fft16<false>(v);
+        const float4 *Hp = reinterpret_cast<const float4 *>(a.H + t * 16);
+#pragma unroll
+        for (int k2 = 0; k2 < 16; k2 += 2) {
+            const float4 h = Hp[k2 >> 1];
+            u[k2] = cmul(v[o16(k2)], make_float2(h.x, h.y));
+            u[k2 + 1] = cmul(v[o16(k2 + 1)], make_float2(h.z, h.w));
+        }
+        fft16<true>(u);
+        const int k1 = t & 15;
+#pragma unroll
+        for (int n0 = 0; n0 < 16; ++n0) {
+            const float2 w = a.tw[16 * k1 * n0];
+            const float2 r = (n0 == 0) ? u[o16(0)] : cmulc(u[o16(n0)], w);      // conj(W_256^(k1 n0))
+            const int p = pad(t * 16 + n0);
+            sm[p] = r;
+        }
+    }
+    __syncthreads();
+    // ---- inverse pass 2 (over k1) inside block k0
+    {
+        const int k0 = t >> 4, n0 = t & 15;
+#pragma unroll
+        for (int k1 = 0; k1 < 16; ++k1) {
+            const int p = pad(k0 * 256 + k1 * 16 + n0);
+            v[k1] = sm[p];
+        }
+        fft16<true>(v);
+        // conj(W_4096^(k0 (16 n1 + n0))) = conj(W^(16 k0 n1) W^(k0 n0)), n1 = 4a + b: W^(16 k0 (4a+b)) from six loads
+        const float2 w0 = a.tw[k0 * n0];
+        float2 wb[4], wa[4];
+        wb[0] = wa[0] = make_float2(1.f, 0.f);
+#pragma unroll
+        for (int i = 1; i < 4; ++i) { wb[i] = a.tw[16 * k0 * i]; wa[i] = a.tw[64 * k0 * i]; }
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) {
+            float2 w = ((n1 & 3) == 0) ? wa[n1 >> 2] : ((n1 >> 2) == 0 ? wb[n1 & 3] : cmul(wa[n1 >> 2], wb[n1 & 3]));
+            w = cmul(w, w0);
+            const float2 r = (k0 == 0) ? v[o16(n1)] : cmulc(v[o16(n1)], w);
+            sm[pad(k0 * 256 + n1 * 16 + n0)] = r;
+        }
+    }
+    __syncthreads();
+    // ---- inverse pass 3 (over k0, stride 256): natural order out; the first K-1 samples of the frame are aliased
+#pragma unroll
+    for (int k0 = 0; k0 < 16; ++k0) {
+        const int p = pad(k0 * 256 + t);
+        v[k0] = sm[p];
+    }
+    fft16<true>(v);
+    const int skip = a.ntaps - 1;
+#pragma unroll
+    for (int n2 = 0; n2 < 16; ++n2) {
+        const int p = n2 * 256 + t;                                // position inside the frame
+        const int64_t o = out0 + (p - skip);
+        if (p >= skip && o < a.n) a.y[o] = v[o16(n2)];
+    }
+}
+
+}  // namespace fft
+
+// ------------------------------------------------------------------------------------------ host
+// Tables for one plan: out[0..4095] = spectrum of the taps / 4096 in digit-reversed order, out[4096..8191] = twiddles.
+int fft_build_tables(const double *taps, int ntaps, float *out /* 2 * 2 * 4096 floats */)
+{
+    using namespace fft;
+    if (ntaps < 2 || ntaps - 1 > N / 2) return -1;
+    const double PI2 = 6.283185307179586476925286766559;
+    // plain O(N K) DFT of the zero-padded taps in float64 (K <= 2049: 8 M complex MACs, once per plan)
+    std::vector<double> c(N), s(N);
+    for (int j = 0; j < N; ++j) {
+        c[j] = cos(PI2 * j / N);
+        s[j] = -sin(PI2 * j / N);
+    }
+    for (int k = 0; k < N; ++k) {
+        double re = 0.0, im = 0.0;
+        for (int n = 0; n < ntaps; ++n) {
+            const int idx = (int)(((long long)k * n) & (N - 1));
+            re += taps[n] * c[idx];
+            im += taps[n] * s[idx];
+        }
+        const int k0 = k & 15, k1 = (k >> 4) & 15, k2 = k >> 8;
+        const int p = k0 * 256 + k1 * 16 + k2;
+        out[2 * p] = (float)(re / N);
+        out[2 * p + 1] = (float)(im / N);
+    }
+    for (int j = 0; j < N; ++j) {
+        out[2 * N + 2 * j] = (float)c[j];
+        out[2 * N + 2 * j + 1] = (float)s[j];
+    }
+    return 0;
+}
+
+int launch_fir_fft(const void *x, const void *hist, void *y, int64_t n, int32_t hist_len, const void *tables_dev,
+                   int ntaps, cudaStream_t stream)
+{
+    using namespace fft;
+    Args a;
+    a.x = static_cast<const float2 *>(x);
+    a.hist = static_cast<const float2 *>(hist);
+    a.y = static_cast<float2 *>(y);
+    a.H = static_cast<const float2 *>(tables_dev);
+    a.tw = a.H + N;
+    a.n = n;
+    a.hist_len = hist_len;
+    a.ntaps = ntaps;
+    a.valid = N - (ntaps - 1);
+    const int64_t frames = (n + a.valid - 1) / a.valid;
+    if (frames > 2147483647LL) {
+        set_error("fir_fft: too many frames (%lld)", (long long)frames);
+        return B200DSP_E_UNSUPPORTED;
+    }
+    fir_fft_os_kernel<<<(unsigned)frames, NT, 0, stream>>>(a);
+    B200_CHECK_LAUNCH("fir_fft_os_kernel");
+    return B200DSP_OK;
+}
+
+}  // namespace b200dsp
