@@ -275,9 +275,10 @@ int tcr_matrix_bytes(int mode, int P);
 int launch_fir_tc_real(int mode, int P, const void *x, const void *hist, void *y, int64_t n, int32_t hist_len,
                        const void *amat_dev, int sb_exp, int ntaps, int sm_count, cudaStream_t stream);
 // fir_fft.cu
+int fft_table_floats();
 int fft_build_tables(const double *taps, int ntaps, float *out);
 int launch_fir_fft(const void *x, const void *hist, void *y, int64_t n, int32_t hist_len, const void *tables_dev,
-                   int ntaps, cudaStream_t stream);
+                   int ntaps, int sm_count, cudaStream_t stream);
 // fir_tc2.cu
 int tc2_build_tap_matrix(const double *taps, int ntaps, unsigned char *out, int *sb_exp);
 int tc2_matrix_bytes();
@@ -511,7 +512,7 @@ static int fir_dispatch(const b200dsp_fir_plan_impl *p, int dtype, const void *x
         // Longer filters (257 .. 2049 taps): overlap-save with the in-shared-memory 4096-point FFT (fir_fft.cu);
         // v == 16 forces it for any filter it can take
         if (L == 1 && M == 1 && p->fft_tables != nullptr && (v == 16 || (v == 0 && p->ntaps > 256 && n >= 32768)))
-            return launch_fir_fft(x, hist, y, n, hist_len, p->fft_tables, p->ntaps, s);
+            return launch_fir_fft(x, hist, y, n, hist_len, p->fft_tables, p->ntaps, p->sm_count, s);
         if (L > 1 && v != 8 && v != 9) {
             const int rc = launch_fir_up_short<float2, 8, true>(p, x, hist, y, n, L, hist_len, s);
             if (rc != B200DSP_E_UNSUPPORTED) return rc;
@@ -591,7 +592,7 @@ int b200dsp_fir_plan_create(const double *taps_host, int32_t ntaps, b200dsp_fir_
     // overlap-save FFT tables (complex64 streams, 2 .. 2049 taps)
     p->fft_tables = nullptr;
     if (e == cudaSuccess && ntaps >= 2 && ntaps <= 2049) {
-        std::vector<float> tb((size_t)4 * 4096);
+        std::vector<float> tb((size_t)fft_table_floats());
         if (fft_build_tables(taps_host, ntaps, tb.data()) == 0) {
             e = cudaMalloc(&p->fft_tables, tb.size() * sizeof(float));
             if (e == cudaSuccess) e = cudaMemcpy(p->fft_tables, tb.data(), tb.size() * sizeof(float), cudaMemcpyHostToDevice);

@@ -13,6 +13,9 @@
 // decimation in time (digit-reversed in, natural order out).  The last forward pass, the product and the first
 // inverse pass work on the same 16 values of a thread, so a frame needs only four shared-memory exchanges.
 // Shared-memory index p -> p + (p >> 4) (one pad word per 16) makes all three access patterns conflict free.
+// The inter-pass twiddles W_4096^(a b) (a < 16, b < 256) and W_256^(k n) live in shared memory too (34 KB, loaded
+// once by a persistent CTA that walks frames with a grid stride): read from a global table they are per-lane
+// gathers, and the first version of this kernel was bound by exactly that (ncu: l1tex throughput 95 %).
 // No cuFFT: the transform, the twiddle tables and the frame logic are all here.
 #include "common.cuh"
 #include <math.h>
@@ -23,14 +26,19 @@ namespace fft {
 
 constexpr int N = 4096;
 constexpr int NT = 256;
-constexpr int SM_FLOATS = N + N / 16;              // padded length of one component array
+constexpr int SM_FLOATS = N + N / 16;              // padded length of the frame buffer (float2 elements)
+constexpr int T1_LEN = 4096, T2_LEN = 256;         // twiddle tables W_4096^(a b) [16][256] and W_256^(k n) [16][16]
+constexpr int TABLE_LEN = N + T1_LEN + T2_LEN;     // float2 elements per plan: spectrum | T1 | T2
+constexpr int SMEM_BYTES = (SM_FLOATS + T1_LEN + T2_LEN) * 8;
+constexpr int CTAS_PER_SM = 3;
 
 struct Args {
     const float2 *x;
     const float2 *hist;
     float2 *y;
     const float2 *H;          // [4096] spectrum of the taps / 4096, digit-reversed order
-    const float2 *tw;         // [4096] exp(-2 pi i j / 4096)
+    const float2 *tw;         // [4096] W_4096^(a b) as [a][b], a < 16, b < 256; then [256] W_256^(k n) as [k][n]
+    int64_t frames;
     int64_t n;
     int32_t hist_len;
     int32_t ntaps;
@@ -87,11 +95,17 @@ __device__ __forceinline__ float2 load_sample(const Args &a, int64_t g)
     return make_float2(0.f, 0.f);
 }
 
-__global__ void __launch_bounds__(NT, 3) fir_fft_os_kernel(const Args a)
+__global__ void __launch_bounds__(NT, CTAS_PER_SM) fir_fft_os_kernel(const Args a)
 {
-    __shared__ float2 sm[SM_FLOATS];                 // (re, im) pairs: 64-bit accesses, conflict free per half-warp
+    extern __shared__ float2 smem_f2[];
+    float2 *sm = smem_f2;                            // frame: (re, im) pairs, 64-bit accesses, conflict free per half-warp
+    float2 *T1 = smem_f2 + SM_FLOATS;
+    float2 *T2 = T1 + T1_LEN;
     const int t = threadIdx.x;
-    const int64_t out0 = (int64_t)blockIdx.x * a.valid;            // first output of this frame
+    for (int i = t; i < T1_LEN + T2_LEN; i += NT) T1[i] = a.tw[i];
+    __syncthreads();
+  for (int64_t frame = blockIdx.x; frame < a.frames; frame += gridDim.x) {
+    const int64_t out0 = frame * a.valid;                          // first output of this frame
     const int64_t g0 = out0 - (a.ntaps - 1);                       // first input sample of the frame
     float2 v[16];
 
@@ -100,19 +114,9 @@ __global__ void __launch_bounds__(NT, 3) fir_fft_os_kernel(const Args a)
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = interior ? a.x[g0 + t + 256 * j] : load_sample(a, g0 + t + 256 * j);
     fft16<false>(v);
-    {
-        // W_4096^(k0 t), k0 = 4a + b, as W^(4a t) W^(b t): six table loads, one product deep
-        float2 wb[4], wa[4];
-        wb[0] = wa[0] = make_float2(1.f, 0.f);
 #pragma unroll
-        for (int i = 1; i < 4; ++i) { wb[i] = a.tw[i * t]; wa[i] = a.tw[4 * i * t]; }
-#pragma unroll
-        for (int k0 = 0; k0 < 16; ++k0) {
-            const float2 w = ((k0 & 3) == 0) ? wa[k0 >> 2] : ((k0 >> 2) == 0 ? wb[k0 & 3] : cmul(wa[k0 >> 2], wb[k0 & 3]));
-            const float2 r = (k0 == 0) ? v[o16(0)] : cmul(v[o16(k0)], w);
-            sm[pad(k0 * 256 + t)] = r;
-        }
-    }
+    for (int k0 = 0; k0 < 16; ++k0)                                // times W_4096^(k0 t)
+        sm[pad(k0 * 256 + t)] = (k0 == 0) ? v[o16(0)] : cmul(v[o16(k0)], T1[k0 * 256 + t]);
     __syncthreads();
     // ---- forward pass 2 (over n1, stride 16) inside block k0
     {
@@ -125,8 +129,7 @@ __global__ void __launch_bounds__(NT, 3) fir_fft_os_kernel(const Args a)
         fft16<false>(v);
 #pragma unroll
         for (int k1 = 0; k1 < 16; ++k1) {          // (a thread rewrites exactly the 16 positions it read: no barrier)
-            const float2 w = a.tw[16 * k1 * n0];                   // W_256^(k1 n0)
-            const float2 r = (k1 == 0) ? v[o16(0)] : cmul(v[o16(k1)], w);
+            const float2 r = (k1 == 0) ? v[o16(0)] : cmul(v[o16(k1)], T2[16 * k1 + n0]);        // W_256^(k1 n0)
             const int p = pad(k0 * 256 + k1 * 16 + n0);
             sm[p] = r;
         }
@@ -152,8 +155,7 @@ __global__ void __launch_bounds__(NT, 3) fir_fft_os_kernel(const Args a)
         const int k1 = t & 15;
 #pragma unroll
         for (int n0 = 0; n0 < 16; ++n0) {
-            const float2 w = a.tw[16 * k1 * n0];
-            const float2 r = (n0 == 0) ? u[o16(0)] : cmulc(u[o16(n0)], w);      // conj(W_256^(k1 n0))
+            const float2 r = (n0 == 0) ? u[o16(0)] : cmulc(u[o16(n0)], T2[16 * n0 + k1]);       // conj(W_256^(k1 n0))
             const int p = pad(t * 16 + n0);
             sm[p] = r;
         }
@@ -168,19 +170,9 @@ __global__ void __launch_bounds__(NT, 3) fir_fft_os_kernel(const Args a)
             v[k1] = sm[p];
         }
         fft16<true>(v);
-        // conj(W_4096^(k0 (16 n1 + n0))) = conj(W^(16 k0 n1) W^(k0 n0)), n1 = 4a + b: W^(16 k0 (4a+b)) from six loads
-        const float2 w0 = a.tw[k0 * n0];
-        float2 wb[4], wa[4];
-        wb[0] = wa[0] = make_float2(1.f, 0.f);
 #pragma unroll
-        for (int i = 1; i < 4; ++i) { wb[i] = a.tw[16 * k0 * i]; wa[i] = a.tw[64 * k0 * i]; }
-#pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1) {
-            float2 w = ((n1 & 3) == 0) ? wa[n1 >> 2] : ((n1 >> 2) == 0 ? wb[n1 & 3] : cmul(wa[n1 >> 2], wb[n1 & 3]));
-            w = cmul(w, w0);
-            const float2 r = (k0 == 0) ? v[o16(n1)] : cmulc(v[o16(n1)], w);
-            sm[pad(k0 * 256 + n1 * 16 + n0)] = r;
-        }
+        for (int n1 = 0; n1 < 16; ++n1)                            // times conj(W_4096^(k0 (16 n1 + n0)))
+            sm[pad(k0 * 256 + n1 * 16 + n0)] = cmulc(v[o16(n1)], T1[k0 * 256 + n1 * 16 + n0]);
     }
     __syncthreads();
     // ---- inverse pass 3 (over k0, stride 256): natural order out; the first K-1 samples of the frame are aliased
@@ -197,13 +189,18 @@ __global__ void __launch_bounds__(NT, 3) fir_fft_os_kernel(const Args a)
         const int64_t o = out0 + (p - skip);
         if (p >= skip && o < a.n) a.y[o] = v[o16(n2)];
     }
+    __syncthreads();                                               // the next frame overwrites the buffer
+  }
 }
 
 }  // namespace fft
 
 // ------------------------------------------------------------------------------------------ host
-// Tables for one plan: out[0..4095] = spectrum of the taps / 4096 in digit-reversed order, out[4096..8191] = twiddles.
-int fft_build_tables(const double *taps, int ntaps, float *out /* 2 * 2 * 4096 floats */)
+// Tables for one plan (fft::TABLE_LEN complex values): the spectrum of the taps / 4096 in digit-reversed order, then
+// the twiddles W_4096^(a b) as [16][256] and W_256^(k n) as [16][16].
+int fft_table_floats() { return 2 * fft::TABLE_LEN; }
+
+int fft_build_tables(const double *taps, int ntaps, float *out /* fft_table_floats() floats */)
 {
     using namespace fft;
     if (ntaps < 2 || ntaps - 1 > N / 2) return -1;
@@ -226,15 +223,21 @@ int fft_build_tables(const double *taps, int ntaps, float *out /* 2 * 2 * 4096 f
         out[2 * p] = (float)(re / N);
         out[2 * p + 1] = (float)(im / N);
     }
-    for (int j = 0; j < N; ++j) {
-        out[2 * N + 2 * j] = (float)c[j];
-        out[2 * N + 2 * j + 1] = (float)s[j];
-    }
+    for (int a = 0; a < 16; ++a)
+        for (int b = 0; b < 256; ++b) {
+            out[2 * (N + a * 256 + b)] = (float)c[(a * b) & (N - 1)];
+            out[2 * (N + a * 256 + b) + 1] = (float)s[(a * b) & (N - 1)];
+        }
+    for (int k = 0; k < 16; ++k)
+        for (int n = 0; n < 16; ++n) {
+            out[2 * (N + T1_LEN + k * 16 + n)] = (float)c[(16 * k * n) & (N - 1)];
+            out[2 * (N + T1_LEN + k * 16 + n) + 1] = (float)s[(16 * k * n) & (N - 1)];
+        }
     return 0;
 }
 
 int launch_fir_fft(const void *x, const void *hist, void *y, int64_t n, int32_t hist_len, const void *tables_dev,
-                   int ntaps, cudaStream_t stream)
+                   int ntaps, int sm_count, cudaStream_t stream)
 {
     using namespace fft;
     Args a;
@@ -247,12 +250,11 @@ int launch_fir_fft(const void *x, const void *hist, void *y, int64_t n, int32_t 
     a.hist_len = hist_len;
     a.ntaps = ntaps;
     a.valid = N - (ntaps - 1);
-    const int64_t frames = (n + a.valid - 1) / a.valid;
-    if (frames > 2147483647LL) {
-        set_error("fir_fft: too many frames (%lld)", (long long)frames);
-        return B200DSP_E_UNSUPPORTED;
-    }
-    fir_fft_os_kernel<<<(unsigned)frames, NT, 0, stream>>>(a);
+    a.frames = (n + a.valid - 1) / a.valid;
+    cudaFuncSetAttribute(fir_fft_os_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);   // per device
+    const int64_t resident = (int64_t)sm_count * CTAS_PER_SM;
+    const unsigned grid = (unsigned)(a.frames < resident ? a.frames : resident);
+    fir_fft_os_kernel<<<grid, NT, SMEM_BYTES, stream>>>(a);
     B200_CHECK_LAUNCH("fir_fft_os_kernel");
     return B200DSP_OK;
 }

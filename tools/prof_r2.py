@@ -36,6 +36,10 @@ elif which == "fir_up12_c64":
 elif which == "fir_dn12_f32":
     plan = _engine.FirPlan(F["b256"]); x = torch.randn(1 << 26, dtype=torch.float32, device=dev)
     fn = lambda: _engine.fir_dn(plan, x, 12)
+elif which == "fir_fft_c64":
+    rng = np.random.default_rng(0)
+    plan = _engine.FirPlan(rng.standard_normal(1024) / 32); x = torch.randn(1 << 26, dtype=torch.complex64, device=dev)
+    fn = lambda: _engine.fir_filter(plan, x)
 else:
     raise SystemExit("unknown " + which)
 for _ in range(4):
