@@ -29,15 +29,15 @@ constexpr int NT = 256;
 constexpr int SM_FLOATS = N + N / 16;              // padded length of the frame buffer (float2 elements)
 constexpr int T1_LEN = 4096, T2_LEN = 256;         // twiddle tables W_4096^(a b) [16][256] and W_256^(k n) [16][16]
 constexpr int TABLE_LEN = N + T1_LEN + T2_LEN;     // float2 elements per plan: spectrum | T1 | T2
-constexpr int SMEM_BYTES = (SM_FLOATS + T1_LEN + T2_LEN) * 8;
-constexpr int CTAS_PER_SM = 3;
+constexpr int SMEM_BYTES = (SM_FLOATS + TABLE_LEN) * 8;           // frame + spectrum + twiddles = 100 KB
+constexpr int CTAS_PER_SM = 2;
 
 struct Args {
     const float2 *x;
     const float2 *hist;
     float2 *y;
-    const float2 *H;          // [4096] spectrum of the taps / 4096, digit-reversed order
-    const float2 *tw;         // [4096] W_4096^(a b) as [a][b], a < 16, b < 256; then [256] W_256^(k n) as [k][n]
+    const float2 *H;          // TABLE_LEN values: spectrum of the taps / 4096 as [k2][k0 * 16 + k1] (k = k0 + 16 k1 + 256 k2),
+                              // W_4096^(a b) as [a][b] (a < 16, b < 256), W_256^(k n) as [k][n]
     int64_t frames;
     int64_t n;
     int32_t hist_len;
@@ -73,9 +73,8 @@ __device__ __forceinline__ void fft16(float2 (&v)[16])
     constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, R2 = 0.70710678118654752f;
     const float2 w1 = make_float2(C1, INV ? S1 : -S1), w2 = make_float2(R2, INV ? R2 : -R2), w3 = make_float2(S1, INV ? C1 : -C1);
     const float2 w6 = make_float2(-R2, INV ? R2 : -R2), w9 = make_float2(-C1, INV ? -S1 : S1);
-    const float2 w4 = make_float2(0.f, INV ? 1.f : -1.f);
     v[1 + 4] = cmul(v[1 + 4], w1);  v[2 + 4] = cmul(v[2 + 4], w2);  v[3 + 4] = cmul(v[3 + 4], w3);      // q = 1: j q = 1,2,3
-    v[1 + 8] = cmul(v[1 + 8], w2);  v[2 + 8] = cmul(v[2 + 8], w4);  v[3 + 8] = cmul(v[3 + 8], w6);      // q = 2: 2,4,6
+    v[1 + 8] = cmul(v[1 + 8], w2);  v[2 + 8] = INV ? make_float2(-v[2 + 8].y, v[2 + 8].x) : make_float2(v[2 + 8].y, -v[2 + 8].x);  v[3 + 8] = cmul(v[3 + 8], w6);      // q = 2: 2,4,6
     v[1 + 12] = cmul(v[1 + 12], w3); v[2 + 12] = cmul(v[2 + 12], w6); v[3 + 12] = cmul(v[3 + 12], w9);  // q = 3: 3,6,9
 #pragma unroll
     for (int q = 0; q < 4; ++q) fft4<INV>(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
@@ -95,24 +94,36 @@ __device__ __forceinline__ float2 load_sample(const Args &a, int64_t g)
     return make_float2(0.f, 0.f);
 }
 
+__device__ __forceinline__ void load_frame(const Args &a, int64_t frame, int t, float2 (&r)[16])
+{
+    const int64_t g0 = frame * a.valid - (a.ntaps - 1);            // first input sample of the frame
+    if (g0 >= 0 && g0 + N <= a.n) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = a.x[g0 + t + 256 * j];
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = load_sample(a, g0 + t + 256 * j);
+    }
+}
+
 __global__ void __launch_bounds__(NT, CTAS_PER_SM) fir_fft_os_kernel(const Args a)
 {
     extern __shared__ float2 smem_f2[];
     float2 *sm = smem_f2;                            // frame: (re, im) pairs, 64-bit accesses, conflict free per half-warp
-    float2 *T1 = smem_f2 + SM_FLOATS;
+    float2 *Hs = smem_f2 + SM_FLOATS;                // spectrum, [k2][k0 * 16 + k1]
+    float2 *T1 = Hs + N;
     float2 *T2 = T1 + T1_LEN;
     const int t = threadIdx.x;
-    for (int i = t; i < T1_LEN + T2_LEN; i += NT) T1[i] = a.tw[i];
+    for (int i = t; i < TABLE_LEN; i += NT) Hs[i] = a.H[i];
+    float2 v[16], nx[16];                            // nx: the next frame's samples, in flight during this frame
+    load_frame(a, blockIdx.x, t, nx);
     __syncthreads();
   for (int64_t frame = blockIdx.x; frame < a.frames; frame += gridDim.x) {
     const int64_t out0 = frame * a.valid;                          // first output of this frame
-    const int64_t g0 = out0 - (a.ntaps - 1);                       // first input sample of the frame
-    float2 v[16];
-
     // ---- forward pass 1 (over n2, stride 256): inputs straight from global memory (coalesced over t)
-    const bool interior = g0 >= 0 && g0 + N <= a.n;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = interior ? a.x[g0 + t + 256 * j] : load_sample(a, g0 + t + 256 * j);
+    for (int j = 0; j < 16; ++j) v[j] = nx[j];
+    if (frame + gridDim.x < a.frames) load_frame(a, frame + gridDim.x, t, nx);
     fft16<false>(v);
 #pragma unroll
     for (int k0 = 0; k0 < 16; ++k0)                                // times W_4096^(k0 t)
@@ -134,7 +145,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) fir_fft_os_kernel(const Args 
             sm[p] = r;
         }
     }
-    __syncthreads();
+    __syncwarp();         // the 16 values thread (k0, k1) reads next were written by threads (k0, 0..15): same half-warp
     // ---- forward pass 3 (over n0), spectrum product, inverse pass 1 (over k2): all on the same 16 values
     {
         float2 u[16];
@@ -144,13 +155,8 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) fir_fft_os_kernel(const Args 
             v[n0] = sm[p];
         }
         fft16<false>(v);
-        const float4 *Hp = reinterpret_cast<const float4 *>(a.H + t * 16);
 #pragma unroll
-        for (int k2 = 0; k2 < 16; k2 += 2) {
-            const float4 h = Hp[k2 >> 1];
-            u[k2] = cmul(v[o16(k2)], make_float2(h.x, h.y));
-            u[k2 + 1] = cmul(v[o16(k2 + 1)], make_float2(h.z, h.w));
-        }
+        for (int k2 = 0; k2 < 16; ++k2) u[k2] = cmul(v[o16(k2)], Hs[k2 * 256 + t]);
         fft16<true>(u);
         const int k1 = t & 15;
 #pragma unroll
@@ -160,7 +166,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) fir_fft_os_kernel(const Args 
             sm[p] = r;
         }
     }
-    __syncthreads();
+    __syncwarp();         // same half-warp again
     // ---- inverse pass 2 (over k1) inside block k0
     {
         const int k0 = t >> 4, n0 = t & 15;
@@ -189,14 +195,14 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) fir_fft_os_kernel(const Args 
         const int64_t o = out0 + (p - skip);
         if (p >= skip && o < a.n) a.y[o] = v[o16(n2)];
     }
-    __syncthreads();                                               // the next frame overwrites the buffer
+    // no barrier: forward pass 1 of the next frame writes exactly the positions this thread has just read
   }
 }
 
 }  // namespace fft
 
 // ------------------------------------------------------------------------------------------ host
-// Tables for one plan (fft::TABLE_LEN complex values): the spectrum of the taps / 4096 in digit-reversed order, then
+// Tables for one plan (fft::TABLE_LEN complex values): the spectrum of the taps / 4096 in the kernel's order, then
 // the twiddles W_4096^(a b) as [16][256] and W_256^(k n) as [16][16].
 int fft_table_floats() { return 2 * fft::TABLE_LEN; }
 
@@ -219,7 +225,7 @@ int fft_build_tables(const double *taps, int ntaps, float *out /* fft_table_floa
             im += taps[n] * s[idx];
         }
         const int k0 = k & 15, k1 = (k >> 4) & 15, k2 = k >> 8;
-        const int p = k0 * 256 + k1 * 16 + k2;
+        const int p = k2 * 256 + k0 * 16 + k1;
         out[2 * p] = (float)(re / N);
         out[2 * p + 1] = (float)(im / N);
     }
@@ -245,7 +251,6 @@ int launch_fir_fft(const void *x, const void *hist, void *y, int64_t n, int32_t 
     a.hist = static_cast<const float2 *>(hist);
     a.y = static_cast<float2 *>(y);
     a.H = static_cast<const float2 *>(tables_dev);
-    a.tw = a.H + N;
     a.n = n;
     a.hist_len = hist_len;
     a.ntaps = ntaps;
