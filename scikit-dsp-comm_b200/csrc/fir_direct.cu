@@ -277,8 +277,8 @@ int launch_fir_tc_real(int mode, int P, const void *x, const void *hist, void *y
 // fir_fft.cu
 int fft_table_floats();
 int fft_build_tables(const double *taps, int ntaps, float *out);
-int launch_fir_fft(const void *x, const void *hist, void *y, int64_t n, int32_t hist_len, const void *tables_dev,
-                   int ntaps, int sm_count, cudaStream_t stream);
+int launch_fir_fft(bool real, const void *x, const void *hist, void *y, int64_t n, int32_t hist_len,
+                   const void *tables_dev, int ntaps, int sm_count, cudaStream_t stream);
 // fir_tc2.cu
 int tc2_build_tap_matrix(const double *taps, int ntaps, unsigned char *out, int *sb_exp);
 int tc2_matrix_bytes();
@@ -490,6 +490,9 @@ static int fir_dispatch(const b200dsp_fir_plan_impl *p, int dtype, const void *x
             return launch_fir_tc_real(mode, P, x, hist, y, n, hist_len, p->tcr_mat[mode][P],
                                       p->tcr_sb[mode][P], p->ntaps, p->sm_count, s);
         }
+        // Longer filters (257 .. 2049 taps): overlap-save FFT, two real frames per complex transform (fir_fft.cu)
+        if (L == 1 && M == 1 && p->fft_tables != nullptr && (v == 16 || (v == 0 && p->ntaps > 256 && n >= 32768)))
+            return launch_fir_fft(true, x, hist, y, n, hist_len, p->fft_tables, p->ntaps, p->sm_count, s);
         if (L > 1 && v != 8 && v != 9) {       // few taps per phase: short-phase kernel (v == 8 / 9: fir_poly_kernel)
             const int rc = launch_fir_up_short<float, 8>(p, x, hist, y, n, L, hist_len, s);
             if (rc != B200DSP_E_UNSUPPORTED) return rc;
@@ -512,7 +515,7 @@ static int fir_dispatch(const b200dsp_fir_plan_impl *p, int dtype, const void *x
         // Longer filters (257 .. 2049 taps): overlap-save with the in-shared-memory 4096-point FFT (fir_fft.cu);
         // v == 16 forces it for any filter it can take
         if (L == 1 && M == 1 && p->fft_tables != nullptr && (v == 16 || (v == 0 && p->ntaps > 256 && n >= 32768)))
-            return launch_fir_fft(x, hist, y, n, hist_len, p->fft_tables, p->ntaps, p->sm_count, s);
+            return launch_fir_fft(false, x, hist, y, n, hist_len, p->fft_tables, p->ntaps, p->sm_count, s);
         if (L > 1 && v != 8 && v != 9) {
             const int rc = launch_fir_up_short<float2, 8, true>(p, x, hist, y, n, L, hist_len, s);
             if (rc != B200DSP_E_UNSUPPORTED) return rc;
@@ -589,7 +592,7 @@ int b200dsp_fir_plan_create(const double *taps_host, int32_t ntaps, b200dsp_fir_
         }
         delete[] h2;
     }
-    // overlap-save FFT tables (complex64 streams, 2 .. 2049 taps)
+    // overlap-save FFT tables (complex64 and float32 streams, 2 .. 2049 taps)
     p->fft_tables = nullptr;
     if (e == cudaSuccess && ntaps >= 2 && ntaps <= 2049) {
         std::vector<float> tb((size_t)fft_table_floats());

@@ -1,4 +1,4 @@
-// fir_fft.cu -- complex64 FIR by overlap-save with a hand-written 4096-point FFT held in shared memory.
+// fir_fft.cu -- complex64 / float32 FIR by overlap-save with a hand-written 4096-point FFT held in shared memory.
 //
 // For filters longer than the 256 taps the block-Toeplitz tensor-core kernel takes, a direct form costs O(K) per
 // sample; overlap-save costs O(log N).  This is the engine behind the reference's FFT block filters
@@ -33,11 +33,12 @@ constexpr int SMEM_BYTES = (SM_FLOATS + TABLE_LEN) * 8;           // frame + spe
 constexpr int CTAS_PER_SM = 2;
 
 struct Args {
-    const float2 *x;
-    const float2 *hist;
-    float2 *y;
-    const float2 *H;          // TABLE_LEN values: spectrum of the taps / 4096 as [k2][k0 * 16 + k1] (k = k0 + 16 k1 + 256 k2),
-                              // W_4096^(a b) as [a][b] (a < 16, b < 256), W_256^(k n) as [k][n]
+    const void *x;            // float2 (complex64) or float (REAL: two consecutive real frames ride as re / im)
+    const void *hist;
+    void *y;
+    const float2 *H;          // TABLE_LEN values, each table [j >> 1][thread index][j & 1] for 128-bit loads:
+                              // spectrum of the taps / 4096 (j = k2, index k0 * 16 + k1, k = k0 + 16 k1 + 256 k2),
+                              // W_4096^(j b) (index b < 256), W_256^(j n) (index n < 16)
     int64_t frames;
     int64_t n;
     int32_t hist_len;
@@ -84,28 +85,58 @@ __device__ __forceinline__ constexpr int o16(int k) { return 4 * (k & 3) + (k >>
 
 __device__ __forceinline__ int pad(int p) { return p + (p >> 4); }
 
-__device__ __forceinline__ float2 load_sample(const Args &a, int64_t g)
+template <typename T>
+__device__ __forceinline__ T load_sample(const Args &a, int64_t g)
 {
-    if (g >= 0) return (g < a.n) ? a.x[g] : make_float2(0.f, 0.f);
+    T z{};
+    if (g >= 0) return (g < a.n) ? static_cast<const T *>(a.x)[g] : z;
     if (a.hist != nullptr) {
         const int64_t h = (int64_t)a.hist_len + g;
-        if (h >= 0) return a.hist[h];
+        if (h >= 0) return static_cast<const T *>(a.hist)[h];
     }
-    return make_float2(0.f, 0.f);
+    return z;
 }
 
+// 16 table values of a thread, stored pair-interleaved ([j >> 1][thread][j & 1]): eight 128-bit loads
+__device__ __forceinline__ void load_pairs(float2 (&w)[16], const float2 *base, int pair_stride)
+{
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+        const float4 q = *reinterpret_cast<const float4 *>(base + (j >> 1) * pair_stride);
+        w[j] = make_float2(q.x, q.y);
+        w[j + 1] = make_float2(q.z, q.w);
+    }
+}
+
+// The 16 samples a thread contributes to a frame.  REAL: the taps are real, so two real frames transform as one
+// complex frame (re = frame 2f, im = frame 2f + 1) and come out of the inverse transform separated again.
+template <bool REAL>
 __device__ __forceinline__ void load_frame(const Args &a, int64_t frame, int t, float2 (&r)[16])
 {
-    const int64_t g0 = frame * a.valid - (a.ntaps - 1);            // first input sample of the frame
-    if (g0 >= 0 && g0 + N <= a.n) {
+    if (!REAL) {
+        const int64_t g0 = frame * a.valid - (a.ntaps - 1);        // first input sample of the frame
+        if (g0 >= 0 && g0 + N <= a.n) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) r[j] = a.x[g0 + t + 256 * j];
+            for (int j = 0; j < 16; ++j) r[j] = static_cast<const float2 *>(a.x)[g0 + t + 256 * j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[j] = load_sample<float2>(a, g0 + t + 256 * j);
+        }
     } else {
+        const int64_t g0 = 2 * frame * a.valid - (a.ntaps - 1);
+        if (g0 >= 0 && g0 + a.valid + N <= a.n) {
+            const float *xa = static_cast<const float *>(a.x) + g0 + t, *xb = xa + a.valid;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) r[j] = load_sample(a, g0 + t + 256 * j);
+            for (int j = 0; j < 16; ++j) r[j] = make_float2(xa[256 * j], xb[256 * j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                r[j] = make_float2(load_sample<float>(a, g0 + t + 256 * j), load_sample<float>(a, g0 + a.valid + t + 256 * j));
+        }
     }
 }
 
+template <bool REAL>
 __global__ void __launch_bounds__(NT, CTAS_PER_SM) fir_fft_os_kernel(const Args a)
 {
     extern __shared__ float2 smem_f2[];
@@ -116,18 +147,21 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) fir_fft_os_kernel(const Args 
     const int t = threadIdx.x;
     for (int i = t; i < TABLE_LEN; i += NT) Hs[i] = a.H[i];
     float2 v[16], nx[16];                            // nx: the next frame's samples, in flight during this frame
-    load_frame(a, blockIdx.x, t, nx);
+    load_frame<REAL>(a, blockIdx.x, t, nx);
     __syncthreads();
   for (int64_t frame = blockIdx.x; frame < a.frames; frame += gridDim.x) {
-    const int64_t out0 = frame * a.valid;                          // first output of this frame
+    const int64_t out0 = (REAL ? 2 : 1) * frame * a.valid;         // first output of this frame (pair)
     // ---- forward pass 1 (over n2, stride 256): inputs straight from global memory (coalesced over t)
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = nx[j];
-    if (frame + gridDim.x < a.frames) load_frame(a, frame + gridDim.x, t, nx);
+    if (frame + gridDim.x < a.frames) load_frame<REAL>(a, frame + gridDim.x, t, nx);
+    // (the tables are read into registers BEFORE each 16-point transform: the compiler cannot hoist a table load
+    //  above the stores to the frame buffer by itself, and with 16 warps per SM an exposed LDS latency shows)
+    float2 w[16];
+    load_pairs(w, T1 + 2 * t, 512);                                // W_4096^(k0 t), k0 = 0..15
     fft16<false>(v);
 #pragma unroll
-    for (int k0 = 0; k0 < 16; ++k0)                                // times W_4096^(k0 t)
-        sm[pad(k0 * 256 + t)] = (k0 == 0) ? v[o16(0)] : cmul(v[o16(k0)], T1[k0 * 256 + t]);
+    for (int k0 = 0; k0 < 16; ++k0) sm[pad(k0 * 256 + t)] = (k0 == 0) ? v[o16(0)] : cmul(v[o16(k0)], w[k0]);
     __syncthreads();
     // ---- forward pass 2 (over n1, stride 16) inside block k0
     {
@@ -137,10 +171,11 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) fir_fft_os_kernel(const Args 
             const int p = pad(k0 * 256 + n1 * 16 + n0);
             v[n1] = sm[p];
         }
+        load_pairs(w, T2 + 2 * n0, 32);                            // W_256^(k1 n0), k1 = 0..15
         fft16<false>(v);
 #pragma unroll
         for (int k1 = 0; k1 < 16; ++k1) {          // (a thread rewrites exactly the 16 positions it read: no barrier)
-            const float2 r = (k1 == 0) ? v[o16(0)] : cmul(v[o16(k1)], T2[16 * k1 + n0]);        // W_256^(k1 n0)
+            const float2 r = (k1 == 0) ? v[o16(0)] : cmul(v[o16(k1)], w[k1]);
             const int p = pad(k0 * 256 + k1 * 16 + n0);
             sm[p] = r;
         }
@@ -154,14 +189,16 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) fir_fft_os_kernel(const Args 
             const int p = pad(t * 16 + n0);
             v[n0] = sm[p];
         }
+        load_pairs(w, Hs + 2 * t, 512);
         fft16<false>(v);
 #pragma unroll
-        for (int k2 = 0; k2 < 16; ++k2) u[k2] = cmul(v[o16(k2)], Hs[k2 * 256 + t]);
-        fft16<true>(u);
+        for (int k2 = 0; k2 < 16; ++k2) u[k2] = cmul(v[o16(k2)], w[k2]);
         const int k1 = t & 15;
+        load_pairs(w, T2 + 2 * k1, 32);                            // W_256^(k1 n0), n0 = 0..15, used conjugated
+        fft16<true>(u);
 #pragma unroll
         for (int n0 = 0; n0 < 16; ++n0) {
-            const float2 r = (n0 == 0) ? u[o16(0)] : cmulc(u[o16(n0)], T2[16 * n0 + k1]);       // conj(W_256^(k1 n0))
+            const float2 r = (n0 == 0) ? u[o16(0)] : cmulc(u[o16(n0)], w[n0]);
             const int p = pad(t * 16 + n0);
             sm[p] = r;
         }
@@ -177,15 +214,17 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) fir_fft_os_kernel(const Args 
         }
         fft16<true>(v);
 #pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1)                            // times conj(W_4096^(k0 (16 n1 + n0)))
-            sm[pad(k0 * 256 + n1 * 16 + n0)] = cmulc(v[o16(n1)], T1[k0 * 256 + n1 * 16 + n0]);
+        for (int n1 = 0; n1 < 16; ++n1) sm[pad(k0 * 256 + n1 * 16 + n0)] = v[o16(n1)];
     }
     __syncthreads();
     // ---- inverse pass 3 (over k0, stride 256): natural order out; the first K-1 samples of the frame are aliased
+    // (the twiddle conj(W_4096^(k0 (16 n1 + n0))) between inverse passes 2 and 3 is applied here, on the input side:
+    //  with 16 n1 + n0 = t it is the same per-thread set W_4096^(k0 t) the first forward pass uses)
+    load_pairs(w, T1 + 2 * t, 512);
 #pragma unroll
     for (int k0 = 0; k0 < 16; ++k0) {
-        const int p = pad(k0 * 256 + t);
-        v[k0] = sm[p];
+        const float2 r = sm[pad(k0 * 256 + t)];
+        v[k0] = (k0 == 0) ? r : cmulc(r, w[k0]);
     }
     fft16<true>(v);
     const int skip = a.ntaps - 1;
@@ -193,7 +232,12 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) fir_fft_os_kernel(const Args 
     for (int n2 = 0; n2 < 16; ++n2) {
         const int p = n2 * 256 + t;                                // position inside the frame
         const int64_t o = out0 + (p - skip);
-        if (p >= skip && o < a.n) a.y[o] = v[o16(n2)];
+        if (!REAL) {
+            if (p >= skip && o < a.n) static_cast<float2 *>(a.y)[o] = v[o16(n2)];
+        } else if (p >= skip) {
+            if (o < a.n) static_cast<float *>(a.y)[o] = v[o16(n2)].x;
+            if (o + a.valid < a.n) static_cast<float *>(a.y)[o + a.valid] = v[o16(n2)].y;
+        }
     }
     // no barrier: forward pass 1 of the next frame writes exactly the positions this thread has just read
   }
@@ -225,41 +269,45 @@ int fft_build_tables(const double *taps, int ntaps, float *out /* fft_table_floa
             im += taps[n] * s[idx];
         }
         const int k0 = k & 15, k1 = (k >> 4) & 15, k2 = k >> 8;
-        const int p = k2 * 256 + k0 * 16 + k1;
+        const int p = (k2 >> 1) * 512 + (k0 * 16 + k1) * 2 + (k2 & 1);
         out[2 * p] = (float)(re / N);
         out[2 * p + 1] = (float)(im / N);
     }
     for (int a = 0; a < 16; ++a)
         for (int b = 0; b < 256; ++b) {
-            out[2 * (N + a * 256 + b)] = (float)c[(a * b) & (N - 1)];
-            out[2 * (N + a * 256 + b) + 1] = (float)s[(a * b) & (N - 1)];
+            const int p = N + (a >> 1) * 512 + b * 2 + (a & 1);
+            out[2 * p] = (float)c[(a * b) & (N - 1)];
+            out[2 * p + 1] = (float)s[(a * b) & (N - 1)];
         }
     for (int k = 0; k < 16; ++k)
         for (int n = 0; n < 16; ++n) {
-            out[2 * (N + T1_LEN + k * 16 + n)] = (float)c[(16 * k * n) & (N - 1)];
-            out[2 * (N + T1_LEN + k * 16 + n) + 1] = (float)s[(16 * k * n) & (N - 1)];
+            const int p = N + T1_LEN + (k >> 1) * 32 + n * 2 + (k & 1);
+            out[2 * p] = (float)c[(16 * k * n) & (N - 1)];
+            out[2 * p + 1] = (float)s[(16 * k * n) & (N - 1)];
         }
     return 0;
 }
 
-int launch_fir_fft(const void *x, const void *hist, void *y, int64_t n, int32_t hist_len, const void *tables_dev,
-                   int ntaps, int sm_count, cudaStream_t stream)
+int launch_fir_fft(bool real, const void *x, const void *hist, void *y, int64_t n, int32_t hist_len,
+                   const void *tables_dev, int ntaps, int sm_count, cudaStream_t stream)
 {
     using namespace fft;
     Args a;
-    a.x = static_cast<const float2 *>(x);
-    a.hist = static_cast<const float2 *>(hist);
-    a.y = static_cast<float2 *>(y);
+    a.x = x;
+    a.hist = hist;
+    a.y = y;
     a.H = static_cast<const float2 *>(tables_dev);
     a.n = n;
     a.hist_len = hist_len;
     a.ntaps = ntaps;
     a.valid = N - (ntaps - 1);
-    a.frames = (n + a.valid - 1) / a.valid;
-    cudaFuncSetAttribute(fir_fft_os_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);   // per device
+    const int64_t per_frame = (real ? 2 : 1) * (int64_t)a.valid;
+    a.frames = (n + per_frame - 1) / per_frame;
+    auto kern = real ? fir_fft_os_kernel<true> : fir_fft_os_kernel<false>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);   // per device
     const int64_t resident = (int64_t)sm_count * CTAS_PER_SM;
     const unsigned grid = (unsigned)(a.frames < resident ? a.frames : resident);
-    fir_fft_os_kernel<<<grid, NT, SMEM_BYTES, stream>>>(a);
+    kern<<<grid, NT, SMEM_BYTES, stream>>>(a);
     B200_CHECK_LAUNCH("fir_fft_os_kernel");
     return B200DSP_OK;
 }

@@ -160,3 +160,67 @@ def test_elementwise_precision_census(filters):
         json.dump(out, open("gpurun_out/precision_census.json", "w"), indent=1)
     except OSError:
         pass
+
+
+def _lowpass(K, fc=0.1):
+    n = np.arange(K) - (K - 1) / 2
+    return np.sinc(2 * fc * n) * np.kaiser(K, 8.0) * 2 * fc
+
+
+@pytest.mark.parametrize("dt", ["complex64", "float32"])
+@pytest.mark.parametrize("K", [2, 33, 257, 1024, 2049])
+def test_fft_overlap_save_kernel(K, dt):
+    """csrc/fir_fft.cu (4096-point FFT in shared memory, overlap-save) against the oracle: forced for any filter
+    it can take (variant 16), with and without a history, on lengths around the frame boundaries"""
+    from sk_dsp_comm_b200 import _engine, _cabi
+    rng = np.random.default_rng(K)
+    b = _lowpass(K) if K > 2 else np.array([0.7, -0.2])
+    plan = _engine.FirPlan(b)
+    valid = 4096 - (K - 1)
+    for n in (1, valid - 1, valid, 2 * valid + 1, 40000, 123457):
+        x = rng.standard_normal(n)
+        hist = rng.standard_normal(K - 1)
+        if dt == "complex64":
+            x = x + 1j * rng.standard_normal(n)
+            hist = hist + 1j * rng.standard_normal(K - 1)
+        x, hist = x.astype(dt), hist.astype(dt)
+        wide = np.complex128 if dt == "complex64" else np.float64
+        _cabi.lib.b200dsp_set_fir_variant(16)
+        try:
+            y = _engine.fir_filter(plan, torch.from_numpy(x).cuda()).cpu().numpy()
+            yh = _engine.fir_filter(plan, torch.from_numpy(x).cuda(), hist=torch.from_numpy(hist).cuda()).cpu().numpy()
+        finally:
+            _cabi.lib.b200dsp_set_fir_variant(0)
+        assert y.dtype == np.dtype(dt) and y.shape == (n,)
+        # a transform's error scales with the frame, not with the local output: a stream shorter than the filter
+        # and without history is only the filter's leading tail (1e-5 of the passband gain), so the bar there is
+        # taken against the filter's full-overlap output level instead
+        ref = oracle.fir_filter(b, x.astype(wide))
+        floor = np.abs(b).sum() * np.abs(x).max() if n < K else 0.0
+        assert float(np.abs(y - ref).max()) <= 1e-6 * max(np.abs(ref).max(), floor), (K, n)
+        assert _rel(yh, oracle.fir_filter(b, x.astype(wide), hist=hist.astype(wide))) <= 1e-6, (K, n)
+
+
+@pytest.mark.parametrize("dt", ["complex64", "float32"])
+def test_long_filter_takes_the_fft_kernel(mrh, dt):
+    """multirate_FIR.filter with more than 256 taps on a long float32 / complex64 stream: the automatic choice is
+    the overlap-save kernel (bit-identical to forcing it) and the result holds the 1e-6 bar"""
+    from sk_dsp_comm_b200 import _engine, _cabi
+    rng = np.random.default_rng(7)
+    b = _lowpass(1024)
+    n = 1 << 20
+    x = rng.standard_normal(n)
+    if dt == "complex64":
+        x = x + 1j * rng.standard_normal(n)
+    x = x.astype(dt)
+    y = mrh.multirate_FIR(b).filter(torch.from_numpy(x).cuda()).cpu().numpy()     # torch input keeps its dtype
+    assert y.dtype == np.dtype(dt)
+    plan = _engine.FirPlan(b)
+    _cabi.lib.b200dsp_set_fir_variant(16)
+    try:
+        yf = _engine.fir_filter(plan, torch.from_numpy(x).cuda()).cpu().numpy()
+    finally:
+        _cabi.lib.b200dsp_set_fir_variant(0)
+    assert np.array_equal(np.asarray(y), yf)
+    ref = oracle.fir_filter(b, x[:200000].astype(np.complex128 if dt == "complex64" else np.float64))
+    assert _rel(np.asarray(y)[:200000], ref) <= 1e-6

@@ -42,6 +42,14 @@ for K in (257, 512, 1024, 2049):
     ms9 = timeit(lambda: _engine.fir_filter(plan, x), reps=2)
     lib.b200dsp_set_fir_variant(0)
     print("K=%4d 2^26 c64: fft %.3f ms (%.3f of HBM), CUDA-core direct %.3f ms" % (K, ms, 16 * (1 << 26) / ms / 1e6 / 6542.1, ms9), flush=True)
+x = torch.randn(1 << 27, dtype=torch.float32, device="cuda")
+for K in (257, 1024, 2049):
+    plan = _engine.FirPlan(lowpass(K))
+    ms = timeit(lambda: _engine.fir_filter(plan, x))
+    lib.b200dsp_set_fir_variant(9)
+    ms9 = timeit(lambda: _engine.fir_filter(plan, x), reps=2)
+    lib.b200dsp_set_fir_variant(0)
+    print("K=%4d 2^27 f32: fft %.3f ms (%.3f of HBM), CUDA-core direct %.3f ms" % (K, ms, 8 * (1 << 27) / ms / 1e6 / 6542.1, ms9), flush=True)
 x = torch.randn(1 << 28, dtype=torch.complex64, device="cuda")
 plan = _engine.FirPlan(np.load(os.path.join(ROOT, "tests/golden/filters.npz"))["b256"])
 ms0 = timeit(lambda: _engine.fir_filter(plan, x))
