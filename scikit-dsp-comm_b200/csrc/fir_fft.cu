@@ -29,8 +29,9 @@ constexpr int NT = 256;
 constexpr int SM_FLOATS = N + N / 16;              // padded length of the frame buffer (float2 elements)
 constexpr int T1_LEN = 4096, T2_LEN = 256;         // twiddle tables W_4096^(a b) [16][256] and W_256^(k n) [16][16]
 constexpr int TABLE_LEN = N + T1_LEN + T2_LEN;     // float2 elements per plan: spectrum | T1 | T2
-constexpr int SMEM_BYTES = (SM_FLOATS + TABLE_LEN) * 8;           // frame + spectrum + twiddles = 100 KB
-constexpr int CTAS_PER_SM = 2;
+constexpr int GROUPS = 3;                          // frames in flight per CTA (256 threads each), sharing the tables
+constexpr int SMEM_BYTES = (GROUPS * SM_FLOATS + TABLE_LEN) * 8;  // 3 x 34 KB frames + 66 KB tables = 168 KB
+constexpr int CTAS_PER_SM = 1;
 
 struct Args {
     const void *x;            // float2 (complex64) or float (REAL: two consecutive real frames ride as re / im)
@@ -80,6 +81,25 @@ __device__ __forceinline__ void fft16(float2 (&v)[16])
 #pragma unroll
     for (int q = 0; q < 4; ++q) fft4<INV>(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 }
+// The transposed form: input x[j] taken from v[4 (j & 3) + (j >> 2)] (where fft16 leaves its outputs), output X[k]
+// in v[k] -- so a forward transform, an element-wise product and an inverse transform chain in place.
+template <bool INV>
+__device__ __forceinline__ void fft16t(float2 (&v)[16])
+{
+#pragma unroll
+    for (int j = 0; j < 4; ++j) fft4<INV>(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    // element (column j, row q) now sits in v[4 j + q]; twiddle W16^(j q)
+    constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, R2 = 0.70710678118654752f;
+    const float2 w1 = make_float2(C1, INV ? S1 : -S1), w2 = make_float2(R2, INV ? R2 : -R2), w3 = make_float2(S1, INV ? C1 : -C1);
+    const float2 w6 = make_float2(-R2, INV ? R2 : -R2), w9 = make_float2(-C1, INV ? -S1 : S1);
+    v[4 + 1] = cmul(v[4 + 1], w1);  v[8 + 1] = cmul(v[8 + 1], w2);  v[12 + 1] = cmul(v[12 + 1], w3);
+    v[4 + 2] = cmul(v[4 + 2], w2);
+    v[8 + 2] = INV ? make_float2(-v[8 + 2].y, v[8 + 2].x) : make_float2(v[8 + 2].y, -v[8 + 2].x);
+    v[12 + 2] = cmul(v[12 + 2], w6);
+    v[4 + 3] = cmul(v[4 + 3], w3);  v[8 + 3] = cmul(v[8 + 3], w6);  v[12 + 3] = cmul(v[12 + 3], w9);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) fft4<INV>(v[q], v[4 + q], v[8 + q], v[12 + q]);
+}
 // position of output k of fft16 inside v
 __device__ __forceinline__ constexpr int o16(int k) { return 4 * (k & 3) + (k >> 2); }
 
@@ -125,9 +145,9 @@ __device__ __forceinline__ void load_frame(const Args &a, int64_t frame, int t, 
     } else {
         const int64_t g0 = 2 * frame * a.valid - (a.ntaps - 1);
         if (g0 >= 0 && g0 + a.valid + N <= a.n) {
-            const float *xa = static_cast<const float *>(a.x) + g0 + t, *xb = xa + a.valid;
+            const float *xa = static_cast<const float *>(a.x) + g0 + t;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) r[j] = make_float2(xa[256 * j], xb[256 * j]);
+            for (int j = 0; j < 16; ++j) r[j] = make_float2(xa[256 * j], xa[256 * j + a.valid]);
         } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
@@ -136,25 +156,25 @@ __device__ __forceinline__ void load_frame(const Args &a, int64_t frame, int t, 
     }
 }
 
+// barrier over the 256 threads of one frame group (named barrier 1 + group)
+__device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory"); }
+
 template <bool REAL>
-__global__ void __launch_bounds__(NT, CTAS_PER_SM) fir_fft_os_kernel(const Args a)
+__global__ void __launch_bounds__(NT * GROUPS, CTAS_PER_SM) fir_fft_os_kernel(const Args a)
 {
     extern __shared__ float2 smem_f2[];
-    float2 *sm = smem_f2;                            // frame: (re, im) pairs, 64-bit accesses, conflict free per half-warp
-    float2 *Hs = smem_f2 + SM_FLOATS;                // spectrum, [k2][k0 * 16 + k1]
+    const int grp = threadIdx.x >> 8, t = threadIdx.x & 255;
+    float2 *sm = smem_f2 + grp * SM_FLOATS;          // frame: (re, im) pairs, 64-bit accesses, conflict free per half-warp
+    float2 *Hs = smem_f2 + GROUPS * SM_FLOATS;       // spectrum
     float2 *T1 = Hs + N;
     float2 *T2 = T1 + T1_LEN;
-    const int t = threadIdx.x;
-    for (int i = t; i < TABLE_LEN; i += NT) Hs[i] = a.H[i];
-    float2 v[16], nx[16];                            // nx: the next frame's samples, in flight during this frame
-    load_frame<REAL>(a, blockIdx.x, t, nx);
+    for (int i = threadIdx.x; i < TABLE_LEN; i += NT * GROUPS) Hs[i] = a.H[i];
+    float2 v[16];
     __syncthreads();
-  for (int64_t frame = blockIdx.x; frame < a.frames; frame += gridDim.x) {
+  for (int64_t frame = (int64_t)blockIdx.x * GROUPS + grp; frame < a.frames; frame += (int64_t)gridDim.x * GROUPS) {
     const int64_t out0 = (REAL ? 2 : 1) * frame * a.valid;         // first output of this frame (pair)
     // ---- forward pass 1 (over n2, stride 256): inputs straight from global memory (coalesced over t)
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = nx[j];
-    if (frame + gridDim.x < a.frames) load_frame<REAL>(a, frame + gridDim.x, t, nx);
+    load_frame<REAL>(a, frame, t, v);
     // (the tables are read into registers BEFORE each 16-point transform: the compiler cannot hoist a table load
     //  above the stores to the frame buffer by itself, and with 16 warps per SM an exposed LDS latency shows)
     float2 w[16];
@@ -162,7 +182,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) fir_fft_os_kernel(const Args 
     fft16<false>(v);
 #pragma unroll
     for (int k0 = 0; k0 < 16; ++k0) sm[pad(k0 * 256 + t)] = (k0 == 0) ? v[o16(0)] : cmul(v[o16(k0)], w[k0]);
-    __syncthreads();
+    group_sync(grp);
     // ---- forward pass 2 (over n1, stride 16) inside block k0
     {
         const int k0 = t >> 4, n0 = t & 15;
@@ -183,7 +203,6 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) fir_fft_os_kernel(const Args 
     __syncwarp();         // the 16 values thread (k0, k1) reads next were written by threads (k0, 0..15): same half-warp
     // ---- forward pass 3 (over n0), spectrum product, inverse pass 1 (over k2): all on the same 16 values
     {
-        float2 u[16];
 #pragma unroll
         for (int n0 = 0; n0 < 16; ++n0) {
             const int p = pad(t * 16 + n0);
@@ -192,13 +211,13 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) fir_fft_os_kernel(const Args 
         load_pairs(w, Hs + 2 * t, 512);
         fft16<false>(v);
 #pragma unroll
-        for (int k2 = 0; k2 < 16; ++k2) u[k2] = cmul(v[o16(k2)], w[k2]);
+        for (int k2 = 0; k2 < 16; ++k2) v[o16(k2)] = cmul(v[o16(k2)], w[k2]);
         const int k1 = t & 15;
         load_pairs(w, T2 + 2 * k1, 32);                            // W_256^(k1 n0), n0 = 0..15, used conjugated
-        fft16<true>(u);
+        fft16t<true>(v);                                           // in place: input where fft16 left it, output natural
 #pragma unroll
         for (int n0 = 0; n0 < 16; ++n0) {
-            const float2 r = (n0 == 0) ? u[o16(0)] : cmulc(u[o16(n0)], w[n0]);
+            const float2 r = (n0 == 0) ? v[0] : cmulc(v[n0], w[n0]);
             const int p = pad(t * 16 + n0);
             sm[p] = r;
         }
@@ -216,7 +235,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) fir_fft_os_kernel(const Args 
 #pragma unroll
         for (int n1 = 0; n1 < 16; ++n1) sm[pad(k0 * 256 + n1 * 16 + n0)] = v[o16(n1)];
     }
-    __syncthreads();
+    group_sync(grp);
     // ---- inverse pass 3 (over k0, stride 256): natural order out; the first K-1 samples of the frame are aliased
     // (the twiddle conj(W_4096^(k0 (16 n1 + n0))) between inverse passes 2 and 3 is applied here, on the input side:
     //  with 16 n1 + n0 = t it is the same per-thread set W_4096^(k0 t) the first forward pass uses)
@@ -227,16 +246,27 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) fir_fft_os_kernel(const Args 
         v[k0] = (k0 == 0) ? r : cmulc(r, w[k0]);
     }
     fft16<true>(v);
-    const int skip = a.ntaps - 1;
-#pragma unroll
-    for (int n2 = 0; n2 < 16; ++n2) {
-        const int p = n2 * 256 + t;                                // position inside the frame
-        const int64_t o = out0 + (p - skip);
+    {
+        // 32-bit bounds: q = position among this frame's outputs, lim = outputs the stream still has room for
+        const int skip = a.ntaps - 1;
+        const int64_t left = a.n - out0;
+        const int lim = left > 2 * N ? 2 * N : (int)left;
+        const int q0 = t - skip;
         if (!REAL) {
-            if (p >= skip && o < a.n) static_cast<float2 *>(a.y)[o] = v[o16(n2)];
-        } else if (p >= skip) {
-            if (o < a.n) static_cast<float *>(a.y)[o] = v[o16(n2)].x;
-            if (o + a.valid < a.n) static_cast<float *>(a.y)[o + a.valid] = v[o16(n2)].y;
+            float2 *yb = static_cast<float2 *>(a.y) + out0 + q0;
+#pragma unroll
+            for (int n2 = 0; n2 < 16; ++n2) {
+                const int q = q0 + n2 * 256;
+                if (q >= 0 && q < lim) yb[n2 * 256] = v[o16(n2)];
+            }
+        } else {
+            float *yb = static_cast<float *>(a.y) + out0 + q0;
+#pragma unroll
+            for (int n2 = 0; n2 < 16; ++n2) {
+                const int q = q0 + n2 * 256;
+                if (q >= 0 && q < lim) yb[n2 * 256] = v[o16(n2)].x;
+                if (q >= 0 && q + a.valid < lim) yb[n2 * 256 + a.valid] = v[o16(n2)].y;
+            }
         }
     }
     // no barrier: forward pass 1 of the next frame writes exactly the positions this thread has just read
@@ -305,9 +335,9 @@ int launch_fir_fft(bool real, const void *x, const void *hist, void *y, int64_t 
     a.frames = (n + per_frame - 1) / per_frame;
     auto kern = real ? fir_fft_os_kernel<true> : fir_fft_os_kernel<false>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);   // per device
-    const int64_t resident = (int64_t)sm_count * CTAS_PER_SM;
-    const unsigned grid = (unsigned)(a.frames < resident ? a.frames : resident);
-    kern<<<grid, NT, SMEM_BYTES, stream>>>(a);
+    const int64_t want = (a.frames + GROUPS - 1) / GROUPS, resident = (int64_t)sm_count * CTAS_PER_SM;
+    const unsigned grid = (unsigned)(want < resident ? want : resident);
+    kern<<<grid, NT * GROUPS, SMEM_BYTES, stream>>>(a);
     B200_CHECK_LAUNCH("fir_fft_os_kernel");
     return B200DSP_OK;
 }
