@@ -6,16 +6,23 @@
 // y = lfilter(h, 1, x) through N-point FFT frames, and behind multirate_FIR.filter
 // (src/sk_dsp_comm/multirate_helper.py:104-109) for long complex64 filters.
 //
-// One CTA (256 threads) per frame: 4096 input samples starting K-1 before the frame's first output, 4096-(K-1)
-// valid outputs.  4096 = 16 x 16 x 16: three radix-16 passes, every thread computing one 16-point DFT in registers
-// per pass.  Forward = decimation in frequency (natural order in, digit-reversed out); the spectrum of the taps is
-// stored in the SAME digit-reversed order (and pre-scaled by 1/4096), so the product needs no reordering; inverse =
+// 256 threads per frame: 4096 input samples starting K-1 before the frame's first output, 4096-(K-1) valid outputs.
+// 4096 = 16 x 16 x 16: three radix-16 passes, every thread computing one 16-point DFT in registers per pass.
+// Forward = decimation in frequency (natural order in, digit-reversed out); the spectrum of the taps is stored in
+// the SAME digit-reversed order (and pre-scaled by 1/4096), so the product needs no reordering; inverse =
 // decimation in time (digit-reversed in, natural order out).  The last forward pass, the product and the first
-// inverse pass work on the same 16 values of a thread, so a frame needs only four shared-memory exchanges.
+// inverse pass work on the same 16 values of a thread, so a frame needs only four shared-memory exchanges, and two
+// of those stay inside a half-warp (warp sync instead of a barrier).
 // Shared-memory index p -> p + (p >> 4) (one pad word per 16) makes all three access patterns conflict free.
-// The inter-pass twiddles W_4096^(a b) (a < 16, b < 256) and W_256^(k n) live in shared memory too (34 KB, loaded
-// once by a persistent CTA that walks frames with a grid stride): read from a global table they are per-lane
-// gathers, and the first version of this kernel was bound by exactly that (ncu: l1tex throughput 95 %).
+// Every table value a thread multiplies by -- spectrum, W_4096^(j t), W_256^(j (t & 15)) -- depends only on the
+// thread index, so the tables are stored per thread, pair-interleaved for 128-bit loads, in shared memory (66 KB):
+// read from a global table they are per-lane gathers, and the first version of this kernel was bound by exactly
+// that (ncu: l1tex throughput 95 %).  A persistent CTA of 768 threads holds ONE copy of the tables and three
+// frames in flight (three independent 256-thread groups on named barriers): 24 warps per SM, 168 KB.
+// (Tried and dropped: 2 CTAs of 256 threads with the next frame prefetched in registers, 0.46 ms against 0.415 at
+//  1024 taps; an L2 prefetch of the next frame, which only added spills.)
+// float32 streams: the taps are real, so two consecutive real frames ride as the real and imaginary part of one
+// complex transform.
 // No cuFFT: the transform, the twiddle tables and the frame logic are all here.
 #include "common.cuh"
 #include <math.h>
