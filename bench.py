@@ -420,8 +420,19 @@ def run_secondary(torch, dev, _engine, b, peak):
           lambda: _engine.sos_filter(splan, x4, M=4), n4, 5)
     del x4
     x5 = torch.randn(1 << 26, dtype=torch.float32, device=dev)
-    timed("cfg4 .up(4) (multirate_IIR.up), 2^26 float32 in", "sos_tc_kernel<12>, zero stuffing fused into the tile load",
+    timed("cfg4 .up(4) (multirate_IIR.up), 2^26 float32 in", "sos_tc_kernel<12>, zero-stuffed stream staged once",
           lambda: _engine.sos_filter(splan, x5, L=4), 1 << 26, 20)
+    del x5
+    # filters beyond the 256 taps of the tensor-core kernel: overlap-save FFT (sigsys.os_filter's method, sigsys.py:482)
+    k = np.arange(1024) - 511.5
+    plan_long = _engine.FirPlan(np.sinc(0.2 * k) * np.kaiser(1024, 8.0) * 0.2)
+    x6 = torch.randn(1 << 26, dtype=torch.complex64, device=dev)
+    timed("multirate_FIR.filter(), 1024 taps, 2^26 complex64", "fir_fft_os_kernel<complex> (4096-point FFT in shared memory, overlap-save)",
+          lambda: _engine.fir_filter(plan_long, x6), 1 << 26, 16)
+    del x6
+    x7 = torch.randn(1 << 27, dtype=torch.float32, device=dev)
+    timed("multirate_FIR.filter(), 1024 taps, 2^27 float32", "fir_fft_os_kernel<real> (two real frames per complex transform)",
+          lambda: _engine.fir_filter(plan_long, x7), 1 << 27, 8)
     return out
 
 
