@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc2_kernel(const Args a)
         // =============================== producer (bulk TMA) ===============================
         int it = 0;
         long long w0 = 0, t_start = DBG ? clock64() : 0;
+        const uint64_t ns_start = DBG ? global_ns() : 0;
         for (int64_t tile = first; tile < a.n_tiles; tile += step, ++it) {
             const int s = it % NSTAGE;
             const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
@@ -192,7 +193,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc2_kernel(const Args a)
             __syncwarp();
         }
         if (DBG && (a.dbg & 8) && blockIdx.x == 1 && lane == 0)
-            printf("tc2 producer: tiles %d total %lld wait_a_empty %lld\n", it, clock64() - t_start, w0);
+            printf("tc2 producer: tiles %d total %lld wait_a_empty %lld  (%llu ns: SM clock %.0f MHz)\n", it, clock64() - t_start, w0,
+                   (unsigned long long)(global_ns() - ns_start), 1e3 * (double)(clock64() - t_start) / (double)(global_ns() - ns_start));
     } else if (warp >= CVT_WARP0 && warp < CVT_WARP0 + N_CVT_WARPS) {
         // =============================== converters ===============================
         const int ct = tid - CVT_WARP0 * 32;
@@ -287,6 +289,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc2_kernel(const Args a)
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t dd = tmem_base + ACC_COL0 + b * ACC_BUF_COLS;
+                    // (M = 64 MMAs for the x_lo pass -- b_hi rows only, dropping the numerically free x_lo*b_lo
+                    //  product -- do not fit this layout: an M = 64 accumulator keeps columns N/2.. in lanes +16 of
+                    //  each quarter and wants the A rows duplicated there, where the b_lo rows live.  Measured with the
+                    //  wrong result: same cycle count, SM clock 1457 instead of 1356 MHz, 8 % faster -- the kernel is
+                    //  limited by the clock the chip sustains under this tensor load, not by issue slots.)
                     // The x_lo stream goes FIRST: its products are ~2^-11 of the result, so the accumulator is
                     // still tiny while they are added and the tensor core's truncating fp32 adds cost nothing;
                     // then x_hi with the small (outer) tap blocks before the large centre ones.

@@ -21,6 +21,8 @@ if what == "err":
     print("order", os.environ.get("B200DSP_TC_ORDER"), "max %.3g rms %.3g | gain alpha %.3g%+.3gj | residual max %.3g rms %.3g (all / max|y|, rms / rms y)" % (
         np.abs(e).max() / np.abs(ref).max(), np.sqrt((np.abs(e) ** 2).mean() / (np.abs(ref) ** 2).mean()), alpha.real, alpha.imag,
         np.abs(res).max() / np.abs(ref).max(), np.sqrt((np.abs(res) ** 2).mean() / (np.abs(ref) ** 2).mean())), flush=True)
+    ec = np.abs(e[:(n // 64) * 64]).reshape(-1, 64).max(axis=0) / np.abs(ref).max()
+    print("  max error by output position mod 64 (x1e-7):", " ".join("%.0f" % (v * 1e7) for v in ec), flush=True)
     # fp32 CUDA-core kernel for comparison
     _cabi.lib.b200dsp_set_fir_variant(0)
     y0 = _engine.fir_filter(plan, torch.from_numpy(x).cuda()).cpu().numpy().astype(np.complex128)
