@@ -283,7 +283,8 @@ int launch_fir_fft(bool real, const void *x, const void *hist, void *y, int64_t 
 int tc2_build_tap_matrix(const double *taps, int ntaps, unsigned char *out, int *sb_exp);
 int tc2_matrix_bytes();
 int launch_fir_tc2(const void *x, const void *hist, void *y, int64_t n, int32_t hist_len,
-                   const void *amat_dev, int sb_exp, int ntaps, int tile_rows, int sm_count, cudaStream_t stream);
+                   const void *amat_dev, int sb_exp, int ntaps, int tile_rows, int sm_count, cudaStream_t stream,
+                   int32_t M = 1);
 
 static thread_local int g_fir_variant = 0;
 
@@ -493,6 +494,12 @@ static int fir_dispatch(const b200dsp_fir_plan_impl *p, int dtype, const void *x
         // Longer filters (257 .. 2049 taps): overlap-save FFT, two real frames per complex transform (fir_fft.cu)
         if (L == 1 && M == 1 && p->fft_tables != nullptr && (v == 16 || (v == 0 && p->ntaps > 256 && n >= 32768)))
             return launch_fir_fft(true, x, hist, y, n, hist_len, p->fft_tables, p->ntaps, p->sm_count, s);
+        // dn(M) the phase-stream kernel above did not take (M > 4 -- the reference's default is 12 -- or more than 65
+        // taps per phase): the tensor-core FILTER kernel with decimating stores.  All outputs are computed, but the
+        // stream is read once at that kernel's rate (3x the polyphase kernel at M = 12).
+        if (L == 1 && M > 1 && v == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && n >= 32768 && tcr_ready(p, 1, 1))
+            return launch_fir_tc_real(1, M, x, hist, y, n, hist_len, p->tcr_mat[1][1], p->tcr_sb[1][1], p->ntaps,
+                                      p->sm_count, s);
         if (L > 1 && v != 8 && v != 9) {       // few taps per phase: short-phase kernel (v == 8 / 9: fir_poly_kernel)
             const int rc = launch_fir_up_short<float, 8>(p, x, hist, y, n, L, hist_len, s);
             if (rc != B200DSP_E_UNSUPPORTED) return rc;
@@ -512,6 +519,12 @@ static int fir_dispatch(const b200dsp_fir_plan_impl *p, int dtype, const void *x
                 return launch_fir_tc2(x, hist, y, n, hist_len, p->tc2_amat, p->tc2_sb_exp, p->ntaps,
                                       v == 13 ? 128 : (v == 12 ? 64 : (v == 15 ? 80 : 96)), p->sm_count, s);
         }
+        // dn(M) on long streams: the same kernel with a decimating epilogue -- every output is computed (an M-phase
+        // tensor-core formulation would do 1/M of the MACs) but the stream is read once at the filter kernel's rate,
+        // 4-5x the CUDA-core polyphase kernel at M = 4 .. 12.  v == 9 forces the CUDA-core kernel.
+        if (L == 1 && M > 1 && p->tc2_amat != nullptr && v == 0 && n >= 32768 && n / M >= 1 &&
+            (reinterpret_cast<uintptr_t>(x) & 15) == 0)
+            return launch_fir_tc2(x, hist, y, n, hist_len, p->tc2_amat, p->tc2_sb_exp, p->ntaps, 96, p->sm_count, s, M);
         // Longer filters (257 .. 2049 taps): overlap-save with the in-shared-memory 4096-point FFT (fir_fft.cu);
         // v == 16 forces it for any filter it can take
         if (L == 1 && M == 1 && p->fft_tables != nullptr && (v == 16 || (v == 0 && p->ntaps > 256 && n >= 32768)))

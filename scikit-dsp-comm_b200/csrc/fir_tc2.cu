@@ -89,6 +89,8 @@ struct Args {
     int32_t sb_exp;
     int32_t jmin;             // first k-block that holds a non-zero tap (short filters skip the rest)
     int32_t dbg;              // bring-up: bit0 skip MMAs, bit1 skip conversion, bit2 skip stores
+    int32_t M;                // DEC kernels: keep every M-th output (multirate_FIR.dn), y[o] = filter output M o
+    int64_t n_m;              // DEC kernels: outputs kept
 };
 
 __device__ __forceinline__ float2 load_sample(const Args &a, int64_t g) {
@@ -104,7 +106,7 @@ __device__ __forceinline__ bool tile_is_bulk(const Args &a, int64_t tile) {
     const int64_t g0 = tile * Cfg<TN>::TILE - HALO;
     return g0 >= 0 && g0 + Cfg<TN>::TILE_IN <= a.n && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0);
 }
-template <int TN, bool DBG>
+template <int TN, bool DBG, bool DEC = false>
 __global__ void __launch_bounds__(NTHREADS, 1) fir_tc2_kernel(const Args a)
 {
     using C = Cfg<TN>;
@@ -345,6 +347,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc2_kernel(const Args a)
             const uint32_t d_re = tmem_base + lane_sel + ACC_COL0 + b_re * ACC_BUF_COLS;
             const uint32_t d_im = tmem_base + lane_sel + ACC_COL0 + b_im * ACC_BUF_COLS;
             const int64_t g_c = tile * TILE + c + (lo_row ? BK : 0);
+            // DEC: this lane's outputs g advance by 2 BK from g_c + 16 BK ch_lo; (gq, rm) = divmod(g, M) follows along
+            int64_t gq = 0;
+            int32_t rm = 0, dq = 0, drm = 0;
+            if constexpr (DEC) {
+                const int64_t g_first = g_c + (int64_t)ch_lo * 16 * BK;
+                gq = g_first / a.M;
+                rm = (int32_t)(g_first - gq * a.M);
+                dq = (2 * BK) / a.M;
+                drm = (2 * BK) - dq * a.M;
+            }
             // real-part accumulator: pull this warp's columns into registers and hand the TMEM slot back
             // immediately -- the MMA warp can refill it while the imaginary part is still being computed
             mbar_wait_t<DBG>(D_FULL(b_re), (unit / NACC) & 1u, 4, w0);
@@ -381,8 +393,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc2_kernel(const Args a)
                         const float ri = __shfl_xor_sync(0xffffffffu, si, 16);
                         const float vr = (rr + __uint_as_float(lo_row ? dr[k][q + 1] : dr[k][q])) * inv;
                         const float vi = (ri + __uint_as_float(lo_row ? di[q + 1] : di[q])) * inv;
-                        const int64_t g = g_c + (int64_t)(c0 + q) * BK;
-                        if ((!DBG || !(a.dbg & 4)) && g < a.n) a.y[g] = make_float2(vr, vi);
+                        if constexpr (DEC) {
+                            if (rm == 0 && gq < a.n_m) a.y[gq] = make_float2(vr, vi);
+                            rm += drm;
+                            gq += dq;
+                            if (rm >= a.M) { rm -= a.M; ++gq; }
+                        } else {
+                            const int64_t g = g_c + (int64_t)(c0 + q) * BK;
+                            if ((!DBG || !(a.dbg & 4)) && g < a.n) a.y[g] = make_float2(vr, vi);
+                        }
                     }
                 }
             }
@@ -433,12 +452,12 @@ int tc2_build_tap_matrix(const double *taps, int ntaps, unsigned char *out, int 
 }
 int tc2_matrix_bytes() { return 128 * tc2::KTOT * 2; }
 
-template <int TN, bool DBG>
+template <int TN, bool DBG, bool DEC = false>
 static int launch_tc2_cfg(tc2::Args a, int64_t n, int sm_count, cudaStream_t stream)
 {
     using namespace tc2;
     a.n_tiles = (n + Cfg<TN>::TILE - 1) / Cfg<TN>::TILE;
-    auto kern = fir_tc2_kernel<TN, DBG>;
+    auto kern = fir_tc2_kernel<TN, DBG, DEC>;
     B200_CHECK_CUDA(allow_smem(kern, Cfg<TN>::SMEM_TOTAL));
     int64_t grid = a.n_tiles < sm_count ? a.n_tiles : sm_count;
     kern<<<(unsigned)grid, NTHREADS, Cfg<TN>::SMEM_TOTAL, stream>>>(a);
@@ -447,10 +466,13 @@ static int launch_tc2_cfg(tc2::Args a, int64_t n, int sm_count, cudaStream_t str
 }
 
 int launch_fir_tc2(const void *x, const void *hist, void *y, int64_t n, int32_t hist_len,
-                   const void *amat_dev, int sb_exp, int ntaps, int tile_rows, int sm_count, cudaStream_t stream)
+                   const void *amat_dev, int sb_exp, int ntaps, int tile_rows, int sm_count, cudaStream_t stream,
+                   int32_t M)
 {
     using namespace tc2;
     Args a;
+    a.M = M;
+    a.n_m = n / M;
     a.x = static_cast<const float2 *>(x);
     a.hist = static_cast<const float2 *>(hist);
     a.y = static_cast<float2 *>(y);
@@ -464,6 +486,9 @@ int launch_fir_tc2(const void *x, const void *hist, void *y, int64_t n, int32_t 
     if (a.jmin < 0) a.jmin = 0;
     a.dbg = 0;
     if (const char *e = getenv("B200DSP_TC_DBG")) a.dbg = atoi(e);
+    // dn(M): the filter runs at the full rate (the tensor work per input sample is what it is) and the epilogue
+    // stores every M-th output; only the samples up to the last kept output are processed
+    if (M > 1) return launch_tc2_cfg<96, false, true>(a, (a.n_m - 1) * M + 1, sm_count, stream);
     if (a.dbg) {
         if (tile_rows == 128) return launch_tc2_cfg<128, true>(a, n, sm_count, stream);
         if (tile_rows == 96) return launch_tc2_cfg<96, true>(a, n, sm_count, stream);

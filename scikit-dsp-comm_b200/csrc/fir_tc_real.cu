@@ -66,6 +66,8 @@ struct Args {
     int32_t sb_exp;
     int32_t jmin;             // filter: first k-block with a non-zero tap
     int32_t dbg;
+    int32_t M;                // <MODE_FILTER, 0> (filter with decimating stores): keep every M-th output
+    int64_t n_dec;            //                                                    outputs kept
 };
 
 __device__ __forceinline__ float load_sample(const Args &a, int64_t g) {
@@ -333,6 +335,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_real_kernel(const Args a)
             tc_fence_after();
             const float inv = tile_inv[it % INV_RING];
             const int64_t m_c = tile * TILE + c + (lo_row ? BK : 0);
+            // filter with decimating stores: the lane's positions advance by 2 BK from m_c; (mq, rm) = divmod(m, M)
+            constexpr bool FDEC = (MODE == MODE_FILTER && P == 0);
+            int64_t mq = 0;
+            int32_t rm = 0, dq = 0, drm = 0;
+            if constexpr (FDEC) {
+                mq = m_c / a.M;
+                rm = (int32_t)(m_c - mq * a.M);
+                dq = (2 * BK) / a.M;
+                drm = (2 * BK) - dq * a.M;
+            }
 #pragma unroll 1
             for (int c0 = 0; c0 < TILE_N; c0 += 16) {
                 uint32_t d[NA][16];
@@ -361,7 +373,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc_real_kernel(const Args a)
                         val[un] = (recv + (lo_row ? own_b : own_a)) * inv;
                     }
                     const int64_t m = m_c + (int64_t)(c0 + q) * BK;          // stream position of this lane's output
-                    if (m < a.n_m && (!DBG || !(a.dbg & 4))) {
+                    if constexpr (FDEC) {
+                        if (rm == 0 && mq < a.n_dec) a.y[mq] = val[0];
+                        rm += drm;
+                        mq += dq;
+                        if (rm >= a.M) { rm -= a.M; ++mq; }
+                    } else if (m < a.n_m && (!DBG || !(a.dbg & 4))) {
                         if (MODE != MODE_UP) {
                             a.y[m] = val[0];
                         } else if (P == 4) {
@@ -458,12 +475,15 @@ static int launch_tcr(tcr::Args a, int sm_count, cudaStream_t stream)
     return B200DSP_OK;
 }
 
-// mode: 1 filter, 2 up (P = L), 3 dn (P = M).  n = input samples.
+// mode: 1 filter, 2 up (P = L), 3 dn (P = M).  n = input samples.  mode 1 with P > 1: the filter kernel with
+// decimating stores (dn by factors that have no phase-stream formulation here): y[o] = filter output P o.
 int launch_fir_tc_real(int mode, int P, const void *x, const void *hist, void *y, int64_t n, int32_t hist_len,
                        const void *amat_dev, int sb_exp, int ntaps, int sm_count, cudaStream_t stream)
 {
     using namespace tcr;
     Args a;
+    a.M = 1;
+    a.n_dec = 0;
     a.x = static_cast<const float *>(x);
     a.hist = static_cast<const float *>(hist);
     a.y = static_cast<float *>(y);
@@ -477,6 +497,13 @@ int launch_fir_tc_real(int mode, int P, const void *x, const void *hist, void *y
     a.dbg = 0;
     if (const char *e = getenv("B200DSP_TC_DBG")) a.dbg = atoi(e);
     if (a.n_m <= 0) return B200DSP_OK;
+    if (mode == MODE_FILTER && P > 1) {
+        a.M = P;
+        a.n_dec = n / P;
+        if (a.n_dec <= 0) return B200DSP_OK;
+        a.n_m = (a.n_dec - 1) * P + 1;              // nothing after the last kept output is computed
+        return launch_tcr<MODE_FILTER, 0>(a, sm_count, stream);
+    }
     if (mode == MODE_FILTER) return launch_tcr<MODE_FILTER, 1>(a, sm_count, stream);
     if (mode == MODE_UP) {
         if (P == 2) return launch_tcr<MODE_UP, 2>(a, sm_count, stream);

@@ -224,3 +224,31 @@ def test_long_filter_takes_the_fft_kernel(mrh, dt):
     assert np.array_equal(np.asarray(y), yf)
     ref = oracle.fir_filter(b, x[:200000].astype(np.complex128 if dt == "complex64" else np.float64))
     assert _rel(np.asarray(y)[:200000], ref) <= 1e-6
+
+
+@pytest.mark.parametrize("dt", ["float32", "complex64"])
+@pytest.mark.parametrize("M", [2, 3, 5, 12, 13])
+def test_dn_decimating_tensor_core_filter(filters, dt, M):
+    """long float32 / complex64 dn(M) the phase-stream kernel does not take runs the tensor-core filter kernel with
+    decimating stores (csrc/fir_tc2.cu DEC, csrc/fir_tc_real.cu <MODE_FILTER, 0>): oracle parity on lengths around
+    the tile and factor boundaries, and agreement with the CUDA-core polyphase kernel (variant 9)"""
+    from sk_dsp_comm_b200 import _engine, _cabi
+    b = filters["b256"]
+    plan = _engine.FirPlan(b)
+    rng = np.random.default_rng(M)
+    for n in (32768, 6144 * 7 + 1, 200003, 12 * 4096 * 5):
+        x = rng.standard_normal(n)
+        if dt == "complex64":
+            x = x + 1j * rng.standard_normal(n)
+        x = x.astype(dt)
+        xt = torch.from_numpy(x).cuda()
+        y = _engine.fir_dn(plan, xt, M).cpu().numpy()
+        _cabi.lib.b200dsp_set_fir_variant(9)
+        try:
+            y9 = _engine.fir_dn(plan, xt, M).cpu().numpy()
+        finally:
+            _cabi.lib.b200dsp_set_fir_variant(0)
+        ref = oracle.fir_dn(b, x.astype(np.complex128 if dt == "complex64" else np.float64), M)
+        assert y.shape == ref.shape == y9.shape and y.dtype == np.dtype(dt)
+        assert _rel(y, ref) <= 1e-6, (M, n)
+        assert _rel(y, y9) <= 2e-6, (M, n)
