@@ -284,7 +284,7 @@ int tc2_build_tap_matrix(const double *taps, int ntaps, unsigned char *out, int 
 int tc2_matrix_bytes();
 int launch_fir_tc2(const void *x, const void *hist, void *y, int64_t n, int32_t hist_len,
                    const void *amat_dev, int sb_exp, int ntaps, int tile_rows, int sm_count, cudaStream_t stream,
-                   int32_t M = 1);
+                   int32_t M = 1, int32_t L = 1);
 
 static thread_local int g_fir_variant = 0;
 
@@ -529,6 +529,13 @@ static int fir_dispatch(const b200dsp_fir_plan_impl *p, int dtype, const void *x
         // v == 16 forces it for any filter it can take
         if (L == 1 && M == 1 && p->fft_tables != nullptr && (v == 16 || (v == 0 && p->ntaps > 256 && n >= 32768)))
             return launch_fir_fft(false, x, hist, y, n, hist_len, p->fft_tables, p->ntaps, p->sm_count, s);
+        // up(L) with more than 32 taps per phase (the short-phase kernel's limit; e.g. 256 taps, L = 2 .. 7): the
+        // tensor-core filter kernel on the zero-stuffed stream.  Only the input samples travel (one small bulk copy
+        // per tile), the converter warps stuff the zeros; L-1 of L MACs multiply zeros, and it is still 2.4x the
+        // CUDA-core polyphase kernel at L = 4 because the stream side runs at the filter kernel's rate.
+        if (L > 1 && M == 1 && v == 0 && p->tc2_amat != nullptr && (p->ntaps + L - 1) / L > 32 && n * L >= 32768 &&
+            (reinterpret_cast<uintptr_t>(x) & 15) == 0)
+            return launch_fir_tc2(x, hist, y, n, hist_len, p->tc2_amat, p->tc2_sb_exp, p->ntaps, 96, p->sm_count, s, 1, L);
         if (L > 1 && v != 8 && v != 9) {
             const int rc = launch_fir_up_short<float2, 8, true>(p, x, hist, y, n, L, hist_len, s);
             if (rc != B200DSP_E_UNSUPPORTED) return rc;

@@ -91,6 +91,8 @@ struct Args {
     int32_t dbg;              // bring-up: bit0 skip MMAs, bit1 skip conversion, bit2 skip stores
     int32_t M;                // DEC kernels: keep every M-th output (multirate_FIR.dn), y[o] = filter output M o
     int64_t n_m;              // DEC kernels: outputs kept
+    int32_t L;                // UP kernels: the stream is x zero-stuffed by L and scaled by L (multirate_FIR.up);
+    int64_t n_in;             //             n = n_in * L is the stream length, x / hist hold input-rate samples
 };
 
 __device__ __forceinline__ float2 load_sample(const Args &a, int64_t g) {
@@ -101,15 +103,45 @@ __device__ __forceinline__ float2 load_sample(const Args &a, int64_t g) {
     }
     return make_float2(0.f, 0.f);
 }
+// UP: stream position g (may be negative: history) of the zero-stuffed, L-scaled input
+__device__ __forceinline__ float2 load_up_sample(const Args &a, int64_t g) {
+    int64_t m = g / a.L;
+    if (m * a.L != g) {
+        if (g >= 0 || (m - 1) * a.L != g) return make_float2(0.f, 0.f);
+        --m;                                           // (unreachable: a multiple of L divides exactly)
+    }
+    float2 v = make_float2(0.f, 0.f);
+    if (m >= 0) {
+        if (m < a.n_in) v = a.x[m];
+    } else if (a.hist != nullptr && (int64_t)a.hist_len + m >= 0) {
+        v = a.hist[(int64_t)a.hist_len + m];
+    }
+    return make_float2(v.x * (float)a.L, v.y * (float)a.L);
+}
+// UP: the input samples x[m0 .. m1) whose positions m L fall inside the staged range of a tile travel compact: one
+// bulk copy of the 16-byte granules [ma, me) that hold them
+struct CompactTile { int64_t ma; int32_t bytes; };
+template <int TN>
+__device__ __forceinline__ bool tile_is_compact(const Args &a, int64_t tile, CompactTile &c) {
+    const int64_t g0 = tile * Cfg<TN>::TILE - HALO;
+    if (g0 < 0 || (reinterpret_cast<uintptr_t>(a.x) & 15) != 0) return false;
+    const int64_t m0 = (g0 + a.L - 1) / a.L, m1 = (g0 + Cfg<TN>::TILE_IN + a.L - 1) / a.L;
+    const int64_t ma = m0 & ~(int64_t)1, me = (m1 + 1) & ~(int64_t)1;
+    if (me > a.n_in) return false;
+    c.ma = ma;
+    c.bytes = (int32_t)(me - ma) * 8;
+    return true;
+}
 template <int TN>
 __device__ __forceinline__ bool tile_is_bulk(const Args &a, int64_t tile) {
     const int64_t g0 = tile * Cfg<TN>::TILE - HALO;
     return g0 >= 0 && g0 + Cfg<TN>::TILE_IN <= a.n && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0);
 }
-template <int TN, bool DBG, bool DEC = false>
+template <int TN, bool DBG, int MODE = 0>      // MODE 0 filter | 1 decimating stores (dn) | 2 zero-stuffed input (up)
 __global__ void __launch_bounds__(NTHREADS, 1) fir_tc2_kernel(const Args a)
 {
     using C = Cfg<TN>;
+    constexpr bool DEC = MODE == 1, UP = MODE == 2;
     constexpr int TILE_N = C::TILE_N, TILE = C::TILE, TILE_IN = C::TILE_IN, RAW_BYTES = C::RAW_BYTES;
     constexpr int STREAM_BYTES = C::STREAM_BYTES, STAGE_BYTES = C::STAGE_BYTES, NSTAGE = C::NSTAGE;
     constexpr int SMEM_BAR_OFF = C::SMEM_BAR_OFF, ACC_BUF_COLS = C::ACC_BUF_COLS, NACC = C::NACC;
@@ -185,7 +217,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc2_kernel(const Args a)
             const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
             mbar_wait_t<DBG>(A_EMPTY(s), ph ^ 1u, 0, w0);
             if (elect_one()) {
-                if (tile_is_bulk<TN>(a, tile)) {
+                CompactTile ctile;
+                if (UP) {
+                    if (tile_is_compact<TN>(a, tile, ctile)) {
+                        mbar_arrive_expect_tx(RAW_FULL(s), (uint32_t)ctile.bytes);
+                        bulk_g2s(base + s * STAGE_BYTES, a.x + ctile.ma, (uint32_t)ctile.bytes, RAW_FULL(s));
+                    } else {
+                        mbar_arrive(RAW_FULL(s));
+                    }
+                } else if (tile_is_bulk<TN>(a, tile)) {
                     mbar_arrive_expect_tx(RAW_FULL(s), RAW_BYTES);
                     bulk_g2s(base + s * STAGE_BYTES, a.x + (tile * TILE - HALO), RAW_BYTES, RAW_FULL(s));
                 } else {
@@ -208,14 +248,48 @@ __global__ void __launch_bounds__(NTHREADS, 1) fir_tc2_kernel(const Args a)
             unsigned char *st = sm + s * STAGE_BYTES;
             mbar_wait_t<DBG>(RAW_FULL(s), ph, 1, w0);
             float4 raw4[F4_PER_THREAD];
-            const bool bulk = tile_is_bulk<TN>(a, tile);
+            const bool bulk = !UP && tile_is_bulk<TN>(a, tile);
             const int64_t g0 = tile * TILE - HALO;
+            // UP, compact tile: stream positions g0 + 2 f (+1) hold x[q] L when r == 0, (q, r) = divmod(position, L)
+            // advancing by 2 N_CVT positions per iteration
+            CompactTile ctile;
+            const bool compact = UP && tile_is_compact<TN>(a, tile, ctile);
+            int32_t qi[2] = {0, 0}, ri[2] = {0, 0}, dq = 0, drm = 0;
+            if (UP && compact) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int64_t pos = g0 + 2 * ct + j, q = pos / a.L;
+                    ri[j] = (int32_t)(pos - q * a.L);
+                    qi[j] = (int32_t)(q - ctile.ma);
+                }
+                dq = (2 * N_CVT) / a.L;
+                drm = (2 * N_CVT) - dq * a.L;
+            }
 #pragma unroll
             for (int i = 0; i < F4_PER_THREAD; ++i) {
                 const int f = ct + i * N_CVT;
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (f < F4_PER_TILE) {
-                    if (bulk) {
+                    if (UP) {
+                        if (compact) {
+                            const float2 *comp = reinterpret_cast<const float2 *>(st);
+                            const float gain = (float)a.L;
+                            float2 e[2];
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                const bool hit = ri[j] == 0;
+                                const float2 cv = comp[hit ? qi[j] : 0];
+                                e[j] = hit ? make_float2(cv.x * gain, cv.y * gain) : make_float2(0.f, 0.f);
+                                ri[j] += drm;
+                                qi[j] += dq;
+                                if (ri[j] >= a.L) { ri[j] -= a.L; ++qi[j]; }
+                            }
+                            v = make_float4(e[0].x, e[0].y, e[1].x, e[1].y);
+                        } else {
+                            const float2 s0 = load_up_sample(a, g0 + 2 * f), s1 = load_up_sample(a, g0 + 2 * f + 1);
+                            v = make_float4(s0.x, s0.y, s1.x, s1.y);
+                        }
+                    } else if (bulk) {
                         v = reinterpret_cast<const float4 *>(st)[f];
                     } else {
                         float2 s0 = load_sample(a, g0 + 2 * f), s1 = load_sample(a, g0 + 2 * f + 1);
@@ -452,12 +526,12 @@ int tc2_build_tap_matrix(const double *taps, int ntaps, unsigned char *out, int 
 }
 int tc2_matrix_bytes() { return 128 * tc2::KTOT * 2; }
 
-template <int TN, bool DBG, bool DEC = false>
+template <int TN, bool DBG, int MODE = 0>
 static int launch_tc2_cfg(tc2::Args a, int64_t n, int sm_count, cudaStream_t stream)
 {
     using namespace tc2;
     a.n_tiles = (n + Cfg<TN>::TILE - 1) / Cfg<TN>::TILE;
-    auto kern = fir_tc2_kernel<TN, DBG, DEC>;
+    auto kern = fir_tc2_kernel<TN, DBG, MODE>;
     B200_CHECK_CUDA(allow_smem(kern, Cfg<TN>::SMEM_TOTAL));
     int64_t grid = a.n_tiles < sm_count ? a.n_tiles : sm_count;
     kern<<<(unsigned)grid, NTHREADS, Cfg<TN>::SMEM_TOTAL, stream>>>(a);
@@ -467,12 +541,15 @@ static int launch_tc2_cfg(tc2::Args a, int64_t n, int sm_count, cudaStream_t str
 
 int launch_fir_tc2(const void *x, const void *hist, void *y, int64_t n, int32_t hist_len,
                    const void *amat_dev, int sb_exp, int ntaps, int tile_rows, int sm_count, cudaStream_t stream,
-                   int32_t M)
+                   int32_t M, int32_t L)
 {
     using namespace tc2;
     Args a;
     a.M = M;
     a.n_m = n / M;
+    a.L = L;
+    a.n_in = n;
+    if (L > 1) n *= L;                                 // the kernel's stream is the zero-stuffed one
     a.x = static_cast<const float2 *>(x);
     a.hist = static_cast<const float2 *>(hist);
     a.y = static_cast<float2 *>(y);
@@ -488,7 +565,8 @@ int launch_fir_tc2(const void *x, const void *hist, void *y, int64_t n, int32_t 
     if (const char *e = getenv("B200DSP_TC_DBG")) a.dbg = atoi(e);
     // dn(M): the filter runs at the full rate (the tensor work per input sample is what it is) and the epilogue
     // stores every M-th output; only the samples up to the last kept output are processed
-    if (M > 1) return launch_tc2_cfg<96, false, true>(a, (a.n_m - 1) * M + 1, sm_count, stream);
+    if (M > 1) return launch_tc2_cfg<96, false, 1>(a, (a.n_m - 1) * M + 1, sm_count, stream);
+    if (L > 1) return launch_tc2_cfg<96, false, 2>(a, n, sm_count, stream);
     if (a.dbg) {
         if (tile_rows == 128) return launch_tc2_cfg<128, true>(a, n, sm_count, stream);
         if (tile_rows == 96) return launch_tc2_cfg<96, true>(a, n, sm_count, stream);

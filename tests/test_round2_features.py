@@ -252,3 +252,33 @@ def test_dn_decimating_tensor_core_filter(filters, dt, M):
         assert y.shape == ref.shape == y9.shape and y.dtype == np.dtype(dt)
         assert _rel(y, ref) <= 1e-6, (M, n)
         assert _rel(y, y9) <= 2e-6, (M, n)
+
+
+@pytest.mark.parametrize("L", [2, 3, 4, 5, 7])
+def test_up_complex64_tensor_core_filter(filters, L):
+    """long complex64 up(L) with more than 32 taps per phase runs the tensor-core filter kernel on the zero-stuffed
+    stream, the converter warps doing the stuffing (csrc/fir_tc2.cu MODE 2): oracle parity with and without history
+    on lengths around the tile boundaries, agreement with the CUDA-core polyphase kernel (variant 9)"""
+    from sk_dsp_comm_b200 import _engine, _cabi
+    b = filters["b256"]
+    plan = _engine.FirPlan(b)
+    rng = np.random.default_rng(L)
+    nh = plan.up_hist_len(L)
+    for n in (32768 // L + 1, 6144 * 3 // L + 5, 50001, 6144 * 4):
+        x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+        hist = (rng.standard_normal(nh) + 1j * rng.standard_normal(nh)).astype(np.complex64)
+        xt = torch.from_numpy(x).cuda()
+        y = _engine.fir_up(plan, xt, L).cpu().numpy()
+        yh = _engine.fir_up(plan, xt, L, hist=torch.from_numpy(hist).cuda()).cpu().numpy()
+        _cabi.lib.b200dsp_set_fir_variant(9)
+        try:
+            y9 = _engine.fir_up(plan, xt, L).cpu().numpy()
+        finally:
+            _cabi.lib.b200dsp_set_fir_variant(0)
+        ref = oracle.fir_up(b, x.astype(np.complex128), L)
+        xe = np.concatenate([hist, x]).astype(np.complex128)
+        refh = oracle.fir_up(b, xe, L)[nh * L:]
+        assert y.shape == ref.shape and y.dtype == np.complex64
+        assert _rel(y, ref) <= 1e-6, (L, n)
+        assert _rel(yh, refh) <= 1e-6, (L, n)
+        assert _rel(y, y9) <= 2e-6, (L, n)
