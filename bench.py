@@ -423,6 +423,23 @@ def run_secondary(torch, dev, _engine, b, peak):
     timed("cfg4 .up(4) (multirate_IIR.up), 2^26 float32 in", "sos_tc_kernel<12>, zero-stuffed stream staged once",
           lambda: _engine.sos_filter(splan, x5, L=4), 1 << 26, 20)
     del x5
+    # the reference's default rate factors L_change = M_change = 12 (multirate_helper.py:112,121), both stream types
+    x8 = torch.randn(1 << 27, dtype=torch.float32, device=dev)
+    timed("multirate_FIR.dn(12), 256 taps, 2^27 float32", "fir_tc_real_kernel<filter> with decimating stores",
+          lambda: _engine.fir_dn(plan, x8, 12), 1 << 27, 4 * 13 / 12)
+    nu = (1 << 27) // 12 // 4 * 4
+    timed("multirate_FIR.up(12), 256 taps, %d float32" % nu, "fir_up_short_kernel (CUDA cores, 22 taps per phase)",
+          lambda: _engine.fir_up(plan, x8[:nu], 12), nu, 4 * 13)
+    del x8
+    x9 = torch.randn(1 << 26, dtype=torch.complex64, device=dev)
+    timed("multirate_FIR.dn(12), 256 taps, 2^26 complex64", "fir_tc2_kernel<96, decimating stores>",
+          lambda: _engine.fir_dn(plan, x9, 12), 1 << 26, 8 * 13 / 12)
+    nu = (1 << 26) // 12 // 4 * 4
+    timed("multirate_FIR.up(12), 256 taps, %d complex64" % nu, "fir_up_short_kernel (CUDA cores, 22 taps per phase)",
+          lambda: _engine.fir_up(plan, x9[:nu], 12), nu, 8 * 13)
+    timed("multirate_FIR.up(4), 256 taps, 2^23 complex64", "fir_tc2_kernel<96, zero-stuffed input>",
+          lambda: _engine.fir_up(plan, x9[:1 << 23], 4), 1 << 23, 8 * 5)
+    del x9
     # filters beyond the 256 taps of the tensor-core kernel: overlap-save FFT (sigsys.os_filter's method, sigsys.py:482)
     k = np.arange(1024) - 511.5
     plan_long = _engine.FirPlan(np.sinc(0.2 * k) * np.kaiser(1024, 8.0) * 0.2)
