@@ -258,7 +258,7 @@ struct b200dsp_fir_plan_impl {
     float *taps_f32;
     double *taps_f64;
     double *taps_host;   // host copy
-    void *tc2_amat;      // taps-stationary tensor-core path: 128 x 320 fp16 matrix for TMEM (or NULL)
+    void *tc2_amat;      // taps-stationary tensor-core path: 128 x (320 | 320 with b_lo rows zero) fp16 for TMEM (or NULL)
     int32_t tc2_sb_exp;
     // float32 tensor-core paths (fir_tc_real.cu): tap matrices per (mode, factor), built on first use
     void *tcr_mat[4][5];      // pointers into tcr_pool
@@ -511,13 +511,14 @@ static int fir_dispatch(const b200dsp_fir_plan_impl *p, int dtype, const void *x
         // v == 10 forces it for any length, v == 9 forces the CUDA-core kernel.
         // Long complex64 streams: block-Toeplitz GEMM on the tensor cores (fir_tc2.cu, taps in TMEM).
         // Needs 16-byte aligned streams (bulk TMA in, vector stores out); otherwise the CUDA-core kernel.
-        //   v == 0 auto (96-row tiles) | 12 / 15 / 14 / 13 force the tensor-core kernel with 64 / 80 / 96 / 128-row
+        //   v == 0 auto (96-row tiles, x_lo pass against zeroed b_lo rows: tile code 97) | 12 / 15 / 14 / 13 force the
+        //   four-product tensor-core kernel with 64 / 80 / 96 / 128-row
         //   tiles | 9 force CUDA cores | 1..5 CUDA-core shapes
         if (L == 1 && M == 1) {
             const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
             if (p->tc2_amat != nullptr && (v == 12 || v == 13 || v == 14 || v == 15 || (v == 0 && n >= 32768 && aligned)))
                 return launch_fir_tc2(x, hist, y, n, hist_len, p->tc2_amat, p->tc2_sb_exp, p->ntaps,
-                                      v == 13 ? 128 : (v == 12 ? 64 : (v == 15 ? 80 : 96)), p->sm_count, s);
+                                      v == 13 ? 128 : (v == 12 ? 64 : (v == 15 ? 80 : (v == 14 ? 96 : 97))), p->sm_count, s);
         }
         // dn(M) on long streams: the same kernel with a decimating epilogue -- every output is computed (an M-phase
         // tensor-core formulation would do 1/M of the MACs) but the stream is read once at the filter kernel's rate,
