@@ -276,6 +276,21 @@ def run_gpu(args):
                 "peak_source": peak_src, "kernel": "fir_tc2_kernel<96> (tcgen05 block-Toeplitz GEMM, taps in TMEM, fp16 hi/lo split)" if args.variant == 0 else "variant %d" % args.variant,
                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SAMPLE * n,
                 "kernel_ms": k_ms, "kernel_ms_min": min(per_step)}
+    if args.variant == 0 and len(b) == 256:
+        # what the tensor cores execute for it: 80 UTCHMMA (128 x 96 x 16) per 6144-sample tile -- three fp16 hi/lo
+        # products (a fourth against zeroed rows) on a 320-wide Toeplitz band for 256 taps -- against the measured
+        # cuBLAS bf16 rates: the kernel sits at the chip's power-limited tensor rate while streaming at `achieved`
+        tiles = (n + 6143) // 6144
+        tflops = 80 * 128 * 96 * 16 * 2 * tiles / (k_ms * 1e-3) / 1e12
+        roofline["tensor_executed"] = {"tflops": tflops, "unit": "TFLOP/s fp16 dense (executed, not algorithmic)"}
+        try:
+            pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            roofline["tensor_executed"].update({
+                "peak_burst": pk["bf16_tflops"], "frac_of_burst": tflops / pk["bf16_tflops"],
+                "peak_sustained": pk.get("bf16_tflops_sustained"),
+                "frac_of_sustained": (tflops / pk["bf16_tflops_sustained"]) if pk.get("bf16_tflops_sustained") else None})
+        except Exception:
+            pass
 
     # ---- parity inside the measured configuration: windows at the shard boundaries vs the oracle -----------
     parity = None
