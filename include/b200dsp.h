@@ -72,7 +72,8 @@ int32_t b200dsp_fir_plan_ntaps(const b200dsp_fir_plan *plan);
  *       or NULL for the reference's zero initial state.  lfilter's zi/zf state is expressed through
  *       hist as well: zf = this call on ntaps-1 zero samples with hist = the block's tail.
  * Also replaces sigsys.os_filter / oa_filter (sigsys.py:482-598), which compute the same output
- * through FFT frames. */
+ * through FFT frames -- as this entry does itself for float32 / complex64 filters of 257..2049 taps
+ * (overlap-save, 4096-point frames, csrc/fir_fft.cu). */
 int b200dsp_fir_filter(const b200dsp_fir_plan *plan, int dtype, const void *x, const void *hist,
                        void *y, int64_t n, void *stream);
 
@@ -94,8 +95,8 @@ int b200dsp_fir_up(const b200dsp_fir_plan *plan, int dtype, const void *x, const
 int32_t b200dsp_fir_up_hist_len(const b200dsp_fir_plan *plan, int32_t L);
 
 /* y[m] = sum_k b[k] * xe[M*m-k], m in [0, floor(n/M)).
- * Replaces multirate_FIR.dn -> downsample(lfilter(b,[1],x), M)  (multirate_helper.py:121-127),
- * computing only the kept outputs.  hist: ntaps-1 preceding samples or NULL. */
+ * Replaces multirate_FIR.dn -> downsample(lfilter(b,[1],x), M)  (multirate_helper.py:121-127); only the kept
+ * outputs are stored (and, on the polyphase kernels, computed).  hist: ntaps-1 preceding samples or NULL. */
 int b200dsp_fir_dn(const b200dsp_fir_plan *plan, int dtype, const void *x, const void *hist,
                    void *y, int64_t n, int32_t M, void *stream);
 
