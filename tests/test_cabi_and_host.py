@@ -111,3 +111,46 @@ def test_segment_bounds():
     assert segs[0][0] == 0 and segs[-1][1] == n
     for (a, b), (c, d) in zip(segs, segs[1:]):
         assert b == c and a % 4 == 0 and c % 4 == 0
+
+
+def test_hostpipe_staging_cache_is_bounded(monkeypatch):
+    """hostpipe keeps its device staging buffers in a small LRU keyed on a power-of-two chunk size (ADVICE.md round 1:
+    one set of buffers per distinct stream length grew device memory without bound).  Host logic only: the buffer
+    class is replaced by a stub, no CUDA call is made."""
+    import torch
+    from sk_dsp_comm_b200 import hostpipe
+
+    made = []
+
+    class FakePipe:
+        def __init__(self, dev, dtype, chunk, k1):
+            self.chunk, self.k1 = chunk, k1
+            made.append(chunk)
+
+    monkeypatch.setattr(hostpipe, "_Pipe", FakePipe)
+    monkeypatch.setattr(hostpipe, "_pipes", {})
+    dev = torch.device("cuda", 0)
+    a = hostpipe._pipe(dev, torch.complex64, 1000000, 255)
+    b = hostpipe._pipe(dev, torch.complex64, 1048576, 255)
+    assert a is b and a.chunk == 1 << 20 and made == [1 << 20]            # same power-of-two bucket: one set of buffers
+    for e in range(11, 11 + 2 * hostpipe._MAX_PIPES):
+        hostpipe._pipe(dev, torch.complex64, 1 << e, 255)
+        assert len(hostpipe._pipes) <= hostpipe._MAX_PIPES
+    keys = list(hostpipe._pipes)
+    hostpipe._pipe(dev, torch.complex64, keys[0][2], 255)                   # touching the oldest makes it the newest
+    assert list(hostpipe._pipes)[-1] == keys[0]
+
+
+def test_numa_binding_is_a_noop_without_topology(monkeypatch):
+    """bind_to_gpu_numa must leave the process alone where the PCI topology is hidden (containers, the VMs the GPU
+    boxes are) instead of raising"""
+    import torch
+    from sk_dsp_comm_b200 import hostpipe
+
+    def boom(_):
+        raise RuntimeError("no CUDA here")
+
+    monkeypatch.setattr(torch.cuda, "get_device_properties", boom)
+    before = os.sched_getaffinity(0)
+    assert hostpipe.bind_to_gpu_numa(0) == {"node": None, "cpus": None}
+    assert os.sched_getaffinity(0) == before
